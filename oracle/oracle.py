@@ -1,0 +1,188 @@
+"""ctypes front-end of the CPU oracle (oracle/libwavelets_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / reference arm.  The product package never imports this.
+
+Arrays are numpy, column-major (Julia layout): an array of Julia size (m, n, d) is
+passed as a Fortran-ordered ndarray of shape (m, n, d).  A trailing batch
+dimension (slices back to back) is supported by the *_batch functions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libwavelets_oracle.so")
+
+ORC_OK, ORC_EDIMS, ORC_ELEVEL, ORC_EPOW2, ORC_EALIAS, ORC_ENOTCUBE, ORC_ETREE = range(7)
+ERRORS = {
+    ORC_EDIMS: "in and out array size must match",
+    ORC_ELEVEL: "L must be positive",
+    ORC_EPOW2: "size must have a sufficient power of 2 factor",
+    ORC_EALIAS: "in array is out array",
+    ORC_ENOTCUBE: "array must be square/cube",
+    ORC_ETREE: "invalid tree",
+}
+MAX_COEF = 8
+
+
+class OracleError(ValueError):
+    def __init__(self, code):
+        super().__init__(ERRORS.get(code, f"oracle error {code}"))
+        self.code = code
+
+
+class Step(C.Structure):
+    _fields_ = [("is_predict", C.c_int32), ("shift", C.c_int32), ("nc", C.c_int32),
+                ("coef", C.c_double * MAX_COEF)]
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with gcc (recipe: oracle/Makefile)."""
+    src_m = max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("wavelets_oracle.c", "oracle_impl.inc"))
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < src_m:
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def _sfx(dtype):
+    dtype = np.dtype(dtype)
+    if dtype == np.float64:
+        return "_f64", C.c_double
+    if dtype == np.float32:
+        return "_f32", C.c_float
+    raise TypeError(f"oracle supports float32/float64, got {dtype}")
+
+
+def make_steps(steps):
+    """steps: iterable of objects/tuples (steptype|is_predict, coef, shift) -> ctypes array."""
+    arr = (Step * len(steps))()
+    for i, s in enumerate(steps):
+        if hasattr(s, "steptype"):
+            is_p, coef, shift = (s.steptype == "predict"), s.coef, s.shift
+        else:
+            is_p, coef, shift = s
+        arr[i].is_predict = 1 if is_p else 0
+        arr[i].shift = int(shift)
+        arr[i].nc = len(coef)
+        for k, c in enumerate(coef):
+            arr[i].coef[k] = float(c)
+    return arr
+
+
+def _dims(shape):
+    return (C.c_int64 * 3)(*(list(shape) + [1] * (3 - len(shape))))
+
+
+def _check(rc):
+    if rc != ORC_OK:
+        raise OracleError(rc)
+
+
+def _fcopy(x):
+    x = np.asarray(x)
+    return np.array(x, dtype=x.dtype, order="F", copy=True)
+
+
+def dwt_filter(x, qmf, L, fw=True):
+    """Reference `dwt(x, OrthoFilter, L)` / `idwt` (1-D/2-D/3-D), out of place."""
+    x = _fcopy(x)
+    sfx, ct = _sfx(x.dtype)
+    y = np.empty_like(x, order="F")
+    q = np.ascontiguousarray(qmf, dtype=np.float64)
+    rc = getattr(lib(), "orc_dwt_filter" + sfx)(
+        y.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), C.c_int(x.ndim), _dims(x.shape),
+        q.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(len(q)), C.c_int(int(L)), C.c_int(1 if fw else 0))
+    _check(rc)
+    return y
+
+
+def dwt_lifting(x, steps, norm1, norm2, L, fw=True):
+    """Reference `dwt(x, GLS, L)` / `idwt`: copy then in-place lifting transform."""
+    y = _fcopy(x)
+    sfx, ct = _sfx(y.dtype)
+    st = make_steps(steps)
+    rc = getattr(lib(), "orc_dwt_lifting" + sfx)(
+        y.ctypes.data_as(C.c_void_p), C.c_int(y.ndim), _dims(y.shape), st, C.c_int(len(st)),
+        C.c_double(norm1), C.c_double(norm2), C.c_int(int(L)), C.c_int(1 if fw else 0))
+    _check(rc)
+    return y
+
+
+def wpt_filter(x, qmf, tree, fw=True):
+    x = np.ascontiguousarray(x)
+    sfx, ct = _sfx(x.dtype)
+    y = np.empty_like(x)
+    q = np.ascontiguousarray(qmf, dtype=np.float64)
+    t = np.ascontiguousarray(tree, dtype=np.uint8)
+    rc = getattr(lib(), "orc_wpt_filter" + sfx)(
+        y.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), C.c_int64(x.shape[0]),
+        q.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(len(q)),
+        t.ctypes.data_as(C.c_void_p), C.c_int64(len(t)), C.c_int(1 if fw else 0))
+    _check(rc)
+    return y
+
+
+def wpt_lifting(x, steps, norm1, norm2, tree, fw=True):
+    y = np.array(x, copy=True)
+    sfx, ct = _sfx(y.dtype)
+    st = make_steps(steps)
+    t = np.ascontiguousarray(tree, dtype=np.uint8)
+    rc = getattr(lib(), "orc_wpt_lifting" + sfx)(
+        y.ctypes.data_as(C.c_void_p), C.c_int64(y.shape[0]), st, C.c_int(len(st)),
+        C.c_double(norm1), C.c_double(norm2), t.ctypes.data_as(C.c_void_p), C.c_int64(len(t)),
+        C.c_int(1 if fw else 0))
+    _check(rc)
+    return y
+
+
+def dwt_filter_batch(x, ndim, qmf, L, fw=True, nthreads=0):
+    """Independent transform of every slice along the last dimension."""
+    x = _fcopy(x)
+    assert x.ndim == ndim + 1
+    sfx, ct = _sfx(x.dtype)
+    y = np.empty_like(x, order="F")
+    q = np.ascontiguousarray(qmf, dtype=np.float64)
+    rc = getattr(lib(), "orc_batch_dwt_filter" + sfx)(
+        y.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), C.c_int(ndim), _dims(x.shape[:ndim]),
+        C.c_int64(x.shape[-1]), q.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(len(q)),
+        C.c_int(int(L)), C.c_int(1 if fw else 0), C.c_int(int(nthreads)))
+    _check(rc)
+    return y
+
+
+def dwt_lifting_batch(x, ndim, steps, norm1, norm2, L, fw=True, nthreads=0):
+    y = _fcopy(x)
+    assert y.ndim == ndim + 1
+    sfx, ct = _sfx(y.dtype)
+    st = make_steps(steps)
+    rc = getattr(lib(), "orc_batch_dwt_lifting" + sfx)(
+        y.ctypes.data_as(C.c_void_p), C.c_int(ndim), _dims(y.shape[:ndim]), C.c_int64(y.shape[-1]),
+        st, C.c_int(len(st)), C.c_double(norm1), C.c_double(norm2),
+        C.c_int(int(L)), C.c_int(1 if fw else 0), C.c_int(int(nthreads)))
+    _check(rc)
+    return y
+
+
+def maxtransformlevels(n: int) -> int:
+    return int(lib().orc_maxtransformlevels(C.c_int64(int(n))))
+
+
+def isvalidtree(n: int, tree) -> bool:
+    t = np.ascontiguousarray(tree, dtype=np.uint8)
+    return bool(lib().orc_isvalidtree(C.c_int64(int(n)), t.ctypes.data_as(C.c_void_p), C.c_int64(len(t))))
