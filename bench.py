@@ -1,0 +1,401 @@
+#!/usr/bin/env python3
+"""bench.py -- Msamples/s of the dwt+idwt pair on B200, next to the CPU reference path.
+
+Contract (see task brief):  python bench.py --gpus N --steps K --warmup W [--impl reference]
+  * N = 1: BASELINE.json configs[1]: 1-D filter-bank dwt + idwt, WT.db4, Float32, N = 2^20, L = 20, a batch of
+    independent columns resident in HBM (batch >> L2, so no L2 flush is needed between iterations).
+  * N > 1 (torchrun, one rank per GPU): every rank owns an equal block of columns (weak scaling, no data-path
+    collective); value = all columns of all ranks / max-over-ranks device time.
+  * one "step" = dwt of the whole batch followed by idwt of the result (the metric is quoted on the pair).
+  * value          : device-resident throughput, CUDA-event timed on the launching stream.
+  * e2e            : same metric through the C ABI's host-buffer entry points (pinned host memory, H2D + D2H
+                     inside the timed region).
+  * roofline       : the dominant kernel's algorithmic bytes (2*sizeof(T) per sample per direction)
+                     / its CUDA-event time inside the timed region, against MEASURED_PEAKS.json hbm_gbs.
+  * cpu_baseline   : the CPU oracle (a restatement of the reference's algorithm; "port") on a bounded sample,
+                     all host cores (OpenMP over columns) -- rank 0, N = 1 only.
+  * --impl reference: times that CPU path alone and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_SIGNAL = 1 << 20
+LEVELS = 20
+METRIC = "Msamples/s dwt+idwt (1-D db4 N=2^20, batched columns)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="columns per GPU (0 = auto from free HBM, <= 8192)")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--e2e-batch", type=int, default=512)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (2-D cdf97, Float64)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks line")
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU reference path (the oracle port of the reference's algorithm), all host cores
+# ------------------------------------------------------------------------------------------------------
+def cpu_pair_rate(dtype_np, seconds, qmf, n=N_SIGNAL, L=LEVELS):
+    """Time dwt+idwt of as many columns as fit in ~`seconds` on all host cores; returns (Msamples/s, cols, cores)."""
+    import numpy as np
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(42)
+    probe = np.asfortranarray(rng.standard_normal((n, cores)).astype(dtype_np))
+    t0 = time.perf_counter()
+    y = orc.dwt_filter_batch(probe, 1, qmf, L, True, cores)
+    orc.dwt_filter_batch(y, 1, qmf, L, False, cores)
+    t_probe = time.perf_counter() - t0
+    reps = max(1, int(seconds / max(t_probe, 1e-3)))
+    cols = cores * min(reps, 16)
+    x = np.asfortranarray(rng.standard_normal((n, cols)).astype(dtype_np))
+    t0 = time.perf_counter()
+    y = orc.dwt_filter_batch(x, 1, qmf, L, True, cores)
+    orc.dwt_filter_batch(y, 1, qmf, L, False, cores)
+    dt = time.perf_counter() - t0
+    return n * cols / dt / 1e6, cols, cores
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path, restated (oracle port), on the host cores."""
+    import numpy as np
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import wavelets_b200 as wb
+    qmf = wb.wavelet(wb.WT.db4).qmf
+    dt_np = np.float32 if args.dtype == "f32" else np.float64
+    from oracle import oracle as orc
+    cores = os.cpu_count() or 1
+    cols = cores * 2
+    rng = np.random.default_rng(42)
+    x = np.asfortranarray(rng.standard_normal((N_SIGNAL, cols)).astype(dt_np))
+
+    def step():
+        y = orc.dwt_filter_batch(x, 1, qmf, LEVELS, True, cores)
+        orc.dwt_filter_batch(y, 1, qmf, LEVELS, False, cores)
+    for _ in range(min(args.warmup, 2)):
+        step()
+    steps = max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    val = N_SIGNAL * cols / dt / 1e6
+    sample = f"{cols} columns of N=2^20 per step (dwt+idwt), OpenMP over columns"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": "1-D db4 filter-bank dwt+idwt, N=2^20, L=20, CPU oracle port of src/Transforms "
+                               "(Julia reference not runnable here: no julia binary)", "columns": cols},
+        "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import wavelets_b200 as wb
+    from wavelets_b200 import _lib
+    from wavelets_b200.shard import allreduce_max
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product has no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    wt = wb.wavelet(wb.WT.db4)
+    qmf = np.ascontiguousarray(wt.qmf)
+    qp = qmf.ctypes.data_as(C.POINTER(C.c_double))
+    tdt = torch.float32 if args.dtype == "f32" else torch.float64
+    code = _lib.F32 if args.dtype == "f32" else _lib.F64
+    esz = 4 if args.dtype == "f32" else 8
+
+    # ---- batch: as many columns as comfortably fit (x, y and the library workspace), capped at 8192 ----
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    B = args.batch
+    if B <= 0:
+        B = 8192
+        while B > 64:
+            need = 2 * N_SIGNAL * B * esz + L.wb200_workspace_bytes(0, 1, _lib.dims_array([N_SIGNAL]), B, LEVELS, code, 0)
+            if need < 0.80 * free_b:
+                break
+            B //= 2
+    dims = _lib.dims_array([N_SIGNAL])
+    ws_bytes = L.wb200_workspace_bytes(0, 1, dims, B, LEVELS, code, 0)
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+    gen = torch.Generator(device=dev); gen.manual_seed(42 + rank)
+    x = torch.empty((B, N_SIGNAL), dtype=tdt, device=dev)
+    for b0 in range(0, B, 256):                                   # randn in slabs: no 2x temporary
+        x[b0:b0 + 256].normal_(generator=gen)
+    y = torch.empty_like(x)
+    stream = torch.cuda.current_stream(dev)
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def step():
+        rc = L.wb200_dwt_filter(y.data_ptr(), x.data_ptr(), 1, dims, B, qp, len(qmf), LEVELS, 1, code,
+                                ws.data_ptr(), ws_bytes, sp, 0)
+        assert rc == 0, L.wb200_last_error_string()
+        rc = L.wb200_dwt_filter(x.data_ptr(), y.data_ptr(), 1, dims, B, qp, len(qmf), LEVELS, 0, code,
+                                ws.data_ptr(), ws_bytes, sp, 0)
+        assert rc == 0, L.wb200_last_error_string()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    L.wb200_launch_count(1)
+    L.wb200_profile_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    L.wb200_profile_enable(0)
+    ms_total = e0.elapsed_time(e1)
+    launches = int(L.wb200_launch_count(1))
+    buf = C.create_string_buffer(1 << 14)
+    nb = L.wb200_profile_collect(buf, len(buf))
+    kern = {}
+    for line in buf.raw[:nb].decode().splitlines():
+        nm, cnt, ms = line.split()
+        kern[nm] = (int(cnt), float(ms))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    ms_step_max = allreduce_max(ms_step, dev) if world > 1 else ms_step
+    value = N_SIGNAL * B * world / (ms_step_max * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel (algorithmic bytes: read n + write n per column per direction) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    roof = None
+    if kern:
+        dom = max(kern, key=lambda k: kern[k][1])
+        cnt, ms = kern[dom]
+        # every kernel name belongs to one direction (analysis / synthesis), so over the timed region it covered
+        # `steps` direction-passes; one pass moves 2*esz bytes per sample algorithmically, whatever the
+        # number of launches the pass is split into (1 for the fused kernel, L for the per-level generic path).
+        alg_bytes_per_pass = 2.0 * esz * N_SIGNAL * B
+        ach = alg_bytes_per_pass * args.steps / (ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": dom, "launches": cnt, "kernel_ms_total": ms,
+                "share_of_step": ms / ms_total, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_direction_pass": alg_bytes_per_pass,
+                "all_kernels_ms": {k: v[1] for k, v in kern.items()}}
+    step_gbs = 4.0 * esz * N_SIGNAL * B / (ms_step * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the C ABI (H2D + D2H inside the timed region) ----
+    e2e = None
+    try:
+        Be = min(args.e2e_batch, B)
+        xh = torch.empty((Be, N_SIGNAL), dtype=tdt).pin_memory()
+        yh = torch.empty((Be, N_SIGNAL), dtype=tdt).pin_memory()
+        xh.copy_(x[:Be])
+
+        def estep():
+            rc = L.wb200_dwt_filter_host(yh.data_ptr(), xh.data_ptr(), 1, dims, Be, qp, len(qmf), LEVELS, 1, code, local_rank, 0)
+            assert rc == 0, L.wb200_last_error_string()
+            rc = L.wb200_dwt_filter_host(xh.data_ptr(), yh.data_ptr(), 1, dims, Be, qp, len(qmf), LEVELS, 0, code, local_rank, 0)
+            assert rc == 0, L.wb200_last_error_string()
+        estep()
+        barrier()
+        ke = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            estep()
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / ke
+        dt_max = allreduce_max(dt, dev) if world > 1 else dt
+        e2e = {"value": N_SIGNAL * Be * world / dt_max / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": 2 * N_SIGNAL * Be * esz, "d2h_bytes_per_step": 2 * N_SIGNAL * Be * esz,
+               "columns_per_gpu": Be, "note": "wb200_dwt_filter_host: pinned host buffers, 3-stream chunk pipeline; "
+               "dwt copies x in / y out, idwt copies y in / x out"}
+        del xh, yh
+    except Exception as ex:                                       # report, never fake
+        e2e = {"value": None, "unit": "Msamples/s", "error": str(ex)[:200]}
+
+    # ---- secondary workloads (reported, not the headline): 2-D cdf97 4096^2 f32 L=8 and the other dtype ----
+    extras = {}
+    if not args.no_extras and world == 1:
+        try:
+            extras = run_extras(L, wb, _lib, dev, stream, args)
+        except Exception as ex:
+            extras = {"error": str(ex)[:300]}
+
+    cpu = None
+    if rank == 0 and world == 1:
+        try:
+            v, cols, cores = cpu_pair_rate(np.float32 if args.dtype == "f32" else np.float64, args.cpu_seconds, qmf)
+            cpu = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port",
+                   "sample": f"{cols} columns of N=2^20 (dwt+idwt), oracle port of src/Transforms, OpenMP over columns"}
+        except Exception as ex:
+            cpu = {"value": None, "unit": "Msamples/s", "error": str(ex)[:200]}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step_max, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"1-D filter-bank dwt+idwt, WT.db4 (8 taps), N=2^20, L=20, {B} columns per GPU "
+                                   f"({'Float32' if esz == 4 else 'Float64'}), BASELINE.json configs[1]",
+                       "columns_per_gpu": B, "parallelism": f"batch-split x{world}",
+                       "l2": f"inputs {2 * N_SIGNAL * B * esz / 2**30:.1f} GiB per step >> 126 MB L2 (no flush needed)"},
+            "achieved_gbs_pair": step_gbs, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks, "extras": extras,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(L, wb, _lib, dev, stream, args):
+    """2-D cdf97 lifting 4096^2 Float32 L=8 (configs[2]; a batch of images so the working set exceeds L2) and the
+    1-D workload in the other precision.  Same timing method, fewer steps."""
+    import numpy as np
+    import torch
+    sp = C.c_void_p(stream.cuda_stream)
+    res = {}
+    wl = wb.wavelet(wb.WT.cdf97, wb.WT.Lifting)
+    steps_arr, ns = _lib.make_steps(wl)
+    n2, Bi = 4096, 16
+    d2 = _lib.dims_array([n2, n2])
+    xi = torch.randn((Bi, n2, n2), dtype=torch.float32, device=dev)
+    yi = torch.empty_like(xi)
+    wsb = L.wb200_workspace_bytes(1, 2, d2, Bi, 8, _lib.F32, 0)
+    wsi = torch.empty(max(wsb, 256), dtype=torch.uint8, device=dev)
+
+    def step2():
+        rc = L.wb200_dwt_lifting(yi.data_ptr(), xi.data_ptr(), 2, d2, Bi, steps_arr, ns, wl.norm1, wl.norm2, 8, 1,
+                                 _lib.F32, wsi.data_ptr(), wsb, sp, 0)
+        assert rc == 0, L.wb200_last_error_string()
+        rc = L.wb200_dwt_lifting(xi.data_ptr(), yi.data_ptr(), 2, d2, Bi, steps_arr, ns, wl.norm1, wl.norm2, 8, 0,
+                                 _lib.F32, wsi.data_ptr(), wsb, sp, 0)
+        assert rc == 0, L.wb200_last_error_string()
+    for _ in range(3):
+        step2()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k = max(3, min(args.steps, 10))
+    e0.record(stream)
+    for _ in range(k):
+        step2()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / k
+    samples = n2 * n2 * Bi
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    gbs = 16.0 * samples / (ms * 1e-3) / 1e9
+    res["dwt2_cdf97_4096x4096_f32_L8"] = {"msamples_per_s_pair": samples / (ms * 1e-3) / 1e6, "images": Bi,
+                                          "ms_per_pair": ms, "achieved_gbs_pair": gbs, "frac_of_hbm_peak": gbs / peak}
+    del xi, yi, wsi
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,424 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, the reference's golden
+vectors and the reference's relational tests (test/transforms.jl, test/gpu.jl).
+
+Tolerances
+  strict mode (WB200_FLAG_STRICT_FP): bit-identical to the oracle (np.array_equal; +0.0 == -0.0).
+  fast mode (FMA contraction)       : Float64  max|d| <= 1e-12 * max(1, max|x|) * levels
+                                      Float32  max|d| <= 1e-5 on N(0,1) data (the reference's own GPU-vs-CPU
+                                      tolerance, test/gpu.jl:24,44)
+  idwt(dwt(x)) round trip           : < 1e-10 (Float64), BASELINE.json north_star
+"""
+import numpy as np
+import pytest
+
+from conftest import wavelet_class, rng
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import wavelets_b200 as wb
+from wavelets_b200 import WT, wavelet, transforms
+from oracle import oracle as orc
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(params=["strict", "fast"])
+def mode(request):
+    wb.set_strict_fp(request.param == "strict")
+    yield request.param
+    wb.set_strict_fp(False)
+
+
+@pytest.fixture(params=["fused", "generic"])
+def path(request):
+    transforms._force_generic(request.param == "generic")
+    yield request.param
+    transforms._force_generic(False)
+
+
+def to_gpu(a, dev):
+    """numpy (logical Julia shape) -> column-major CUDA tensor"""
+    return wb.colmajor(torch.tensor(np.ascontiguousarray(a), device=dev))
+
+
+def to_np(t):
+    return t.cpu().numpy()
+
+
+def check(gpu, ref, mode, levels=1, scale=1.0):
+    gpu = to_np(gpu) if isinstance(gpu, torch.Tensor) else gpu
+    assert gpu.shape == ref.shape and gpu.dtype == ref.dtype
+    if mode == "strict":
+        assert np.array_equal(gpu, ref), f"strict mode not bit-identical: max|d|={np.max(np.abs(gpu - ref)):.3e}"
+    else:
+        tol = 1e-5 if ref.dtype == np.float32 else 1e-12 * max(1.0, scale) * max(1, levels)
+        err = float(np.max(np.abs(gpu.astype(np.float64) - ref.astype(np.float64)))) if ref.size else 0.0
+        assert err <= tol, f"max|d|={err:.3e} > {tol:.1e}"
+
+
+# ------------------------------------------------------------------------------------------------------
+# golden vectors (test/transforms.jl:2-55)
+# ------------------------------------------------------------------------------------------------------
+def test_golden_vectors_gpu(golden, dev, mode, path):
+    x = np.array(golden["data1d"]); x2 = np.array(golden["data2d"])
+    tol1, tol2 = 1e-9 * np.sqrt(x.size), 1e-9 * np.sqrt(x2.size)
+    xg, x2g = to_gpu(x, dev), to_gpu(x2, dev)
+    for key in sorted(golden["expected1d"]):
+        wt = wavelet(wavelet_class(key))
+        y = wb.dwt(xg, wt)
+        y2 = wb.dwt(x2g, wt)
+        assert np.linalg.norm(to_np(y) - np.array(golden["expected1d"][key])) <= tol1, key
+        assert np.linalg.norm(to_np(y2) - np.array(golden["expected2d"][key])) <= tol2, key
+        check(y, orc.dwt_filter(x, wt.qmf, 6), mode, 6, 4.0)
+        check(y2, orc.dwt_filter(x2, wt.qmf, 3), mode, 3, 4.0)
+        check(wb.idwt(y, wt), orc.dwt_filter(to_np(y), wt.qmf, 6, fw=False), mode, 6, 4.0)
+        check(wb.idwt(y2, wt), orc.dwt_filter(to_np(y2), wt.qmf, 3, fw=False), mode, 3, 4.0)
+
+
+def test_golden_nonsquare(golden, dev, mode):
+    x = np.array(golden["nonsquare_data"])
+    y = wb.dwt(to_gpu(x, dev), wavelet(WT.haar), 1)
+    assert np.linalg.norm(to_np(y) - np.array(golden["nonsquare_haar_L1"])) <= 1e-9 * np.sqrt(x.size)
+    check(y, orc.dwt_filter(x, wavelet(WT.haar).qmf, 1), mode)
+
+
+# ------------------------------------------------------------------------------------------------------
+# filter path vs oracle: sizes, dtypes, dimensions, levels
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape,L", [((1024,), 10), ((1024,), 3), ((24,), 3), ((40,), 2), ((2,), 1), ((4,), 2),
+                                     ((32, 32), 5), ((16, 64), 3), ((48, 24), 3), ((16, 16, 16), 4),
+                                     ((8, 16, 32), 2), ((4096,), 12)])
+@pytest.mark.parametrize("wname", ["db2", "db4", "sym8", "haar", "batt2"])
+def test_filter_vs_oracle(dev, mode, path, dtype, shape, L, wname):
+    wt = wavelet(wavelet_class(wname))
+    x = rng(hash((shape, L, wname)) % 2**31).standard_normal(shape).astype(dtype)
+    y = wb.dwt(to_gpu(x, dev), wt, L)
+    ref = orc.dwt_filter(x, wt.qmf, L)
+    check(y, ref, mode, L, 4.0)
+    xr = wb.idwt(y, wt, L)
+    check(xr, orc.dwt_filter(to_np(y), wt.qmf, L, fw=False), mode, L, 4.0)
+    if dtype == np.float64 and wname != "batt2":   # Battle filters are only approximately orthogonal
+        assert float(np.max(np.abs(to_np(xr) - x))) < 1e-10
+
+
+def test_config1_db2_n1024_float64(dev):
+    """BASELINE config 1: dwt(x, wavelet(WT.db2)) Float64 N=1024 L=full, bit-compare (strict mode)."""
+    wt = wavelet(WT.db2)
+    x = rng(42).standard_normal(1024)
+    wb.set_strict_fp(True)
+    try:
+        y = wb.dwt(to_gpu(x, dev), wt)
+    finally:
+        wb.set_strict_fp(False)
+    assert np.array_equal(to_np(y), orc.dwt_filter(x, wt.qmf, 10))
+
+
+def test_tiny_lines_multiwrap(dev, mode, path):
+    """n < flen: every tap wraps several times (59-tap Battle on n = 2, 4, 8)."""
+    for wname in ("batt6", "batt4", "coif10", "vaid"):
+        wt = wavelet(wavelet_class(wname))
+        for n in (2, 4, 8, 16):
+            x = rng(n).standard_normal(n)
+            L = wb.maxtransformlevels(n)
+            y = wb.dwt(to_gpu(x, dev), wt, L)
+            check(y, orc.dwt_filter(x, wt.qmf, L), mode, L, 4.0)
+            check(wb.idwt(y, wt, L), orc.dwt_filter(to_np(y), wt.qmf, L, fw=False), mode, L, 4.0)
+
+
+def test_level_zero_and_empty_batch(dev):
+    wt = wavelet(WT.db4)
+    x = to_gpu(rng(1).standard_normal(64), dev)
+    assert torch.equal(wb.dwt(x, wt, 0), x)
+    xb = torch.empty((64, 0), device=dev, dtype=torch.float64)
+    assert wb.dwtc(xb, wt).shape == (64, 0)
+
+
+# ------------------------------------------------------------------------------------------------------
+# lifting path
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape,L", [((64,), 6), ((1024,), 10), ((24,), 3), ((2,), 1), ((4,), 2), ((4096,), 5),
+                                     ((32, 32), 5), ((128, 128), 3), ((16, 16, 16), 4), ((32, 32, 32), 2)])
+@pytest.mark.parametrize("wname", ["cdf97", "db2", "haar"])
+def test_lifting_vs_oracle(dev, mode, path, dtype, shape, L, wname):
+    wl = wavelet(getattr(WT, wname), WT.Lifting)
+    x = rng(hash((shape, L, wname)) % 2**31).standard_normal(shape).astype(dtype)
+    y = wb.dwt(to_gpu(x, dev), wl, L)
+    ref = orc.dwt_lifting(x, wl.step, wl.norm1, wl.norm2, L)
+    check(y, ref, mode, 2 * L, 8.0)
+    xr = wb.idwt(y, wl, L)
+    check(xr, orc.dwt_lifting(to_np(y), wl.step, wl.norm1, wl.norm2, L, fw=False), mode, 2 * L, 8.0)
+    if dtype == np.float64:
+        assert float(np.max(np.abs(to_np(xr) - x))) < 1e-10
+    # in-place form dwt!(y, scheme, L)
+    yin = to_gpu(x, dev).clone(memory_format=torch.preserve_format)
+    yin = wb.colmajor(yin)
+    wb.dwt_(yin, wl, L)
+    check(yin, ref, mode, 2 * L, 8.0)
+
+
+@pytest.mark.parametrize("wclass", ["db1", "db2"])
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_lifting_equals_filter_gpu(dev, wclass, ndim):
+    """test/transforms.jl:57-128 on the CUDA path."""
+    n = 32
+    c = getattr(WT, wclass)
+    wf, wl = wavelet(c, WT.Filter), wavelet(c, WT.Lifting)
+    x = rng(7).standard_normal((n,) * ndim)
+    xg = to_gpu(x, dev)
+    tol = 1e-10 * np.sqrt(x.size)
+    for L in (5, 0, 1, 2):
+        yf, yl = wb.dwt(xg, wf, L), wb.dwt(xg, wl, L)
+        assert float(torch.linalg.norm((yf - yl).flatten())) <= tol
+        assert float(torch.linalg.norm((wb.idwt(yf, wf, L) - xg).flatten())) <= tol
+        assert float(torch.linalg.norm((wb.idwt(yl, wl, L) - xg).flatten())) <= tol
+
+
+def test_haar_integer_lifting_bit_exact(dev, path):
+    """north_star: bit-exact for Haar integer lifting -- in BOTH fp modes."""
+    wl = wavelet(WT.haar, WT.Lifting)
+    xi = rng(9).integers(-100000, 100000, size=(4096,))
+    ref = orc.dwt_lifting(xi.astype(np.float64), wl.step, wl.norm1, wl.norm2, 12)
+    for strict in (True, False):
+        wb.set_strict_fp(strict)
+        y = wb.dwt(torch.tensor(xi, device=dev), wl)          # Int64 input -> float(x)
+        wb.set_strict_fp(False)
+        assert y.dtype == torch.float64
+        assert np.array_equal(to_np(y), ref)
+    img = rng(10).integers(-255, 255, size=(64, 64)).astype(np.float32)
+    y2 = wb.dwt(to_gpu(img, dev), wl, 1)
+    assert np.array_equal(to_np(y2), orc.dwt_lifting(img, wl.step, wl.norm1, wl.norm2, 1))
+
+
+# ------------------------------------------------------------------------------------------------------
+# batches, complex, integer input
+# ------------------------------------------------------------------------------------------------------
+def test_dwtc_batch_matches_per_column(dev, mode, path):
+    wt = wavelet(WT.db4)
+    x = rng(11).standard_normal((2048, 7))
+    y = wb.dwtc(to_gpu(x, dev), wt)
+    check(y, orc.dwt_filter_batch(x, 1, wt.qmf, 11), mode, 11, 4.0)
+    check(wb.idwtc(y, wt), orc.dwt_filter_batch(to_np(y), 1, wt.qmf, 11, fw=False), mode, 11, 4.0)
+    wl = wavelet(WT.cdf97, WT.Lifting)
+    imgs = rng(12).standard_normal((64, 64, 5)).astype(np.float32)
+    yi = wb.dwtc(to_gpu(imgs, dev), wl, 4)
+    check(yi, orc.dwt_lifting_batch(imgs, 2, wl.step, wl.norm1, wl.norm2, 4), mode, 8, 8.0)
+    yf = wb.dwtc(to_gpu(imgs, dev), wt, 3)
+    check(yf, orc.dwt_filter_batch(imgs, 2, wt.qmf, 3), mode, 6, 8.0)
+
+
+@pytest.mark.parametrize("shape,L", [((64,), 6), ((16, 16), 3), ((8, 8, 8), 2)])
+def test_complex(dev, mode, shape, L):
+    """ComplexF64 works for filter and lifting in the reference (test/transforms.jl:154-160)."""
+    r = rng(13)
+    x = r.standard_normal(shape) + 1j * r.standard_normal(shape)
+    wt = wavelet(WT.db3)
+    y = to_np(wb.dwt(to_gpu(x, dev), wt, L))
+    check(np.ascontiguousarray(y.real), np.ascontiguousarray(orc.dwt_filter(x.real.copy(), wt.qmf, L)), mode, L, 4.0)
+    check(np.ascontiguousarray(y.imag), np.ascontiguousarray(orc.dwt_filter(x.imag.copy(), wt.qmf, L)), mode, L, 4.0)
+    xr = to_np(wb.idwt(to_gpu(y, dev), wt, L))
+    assert np.max(np.abs(xr - x)) < 1e-10
+    wl = wavelet(WT.db2, WT.Lifting)
+    yl = to_np(wb.dwt(to_gpu(x, dev), wl, L))
+    check(np.ascontiguousarray(yl.real), np.ascontiguousarray(orc.dwt_lifting(x.real.copy(), wl.step, wl.norm1, wl.norm2, L)), mode, 2 * L, 8.0)
+    check(np.ascontiguousarray(yl.imag), np.ascontiguousarray(orc.dwt_lifting(x.imag.copy(), wl.step, wl.norm1, wl.norm2, L)), mode, 2 * L, 8.0)
+
+
+def test_types(dev):
+    """eltype preserved for Float32/Float64, Int -> float (test/transforms.jl:130-201)."""
+    wt = wavelet(WT.db2)
+    for dt, out in ((torch.float32, torch.float32), (torch.float64, torch.float64),
+                    (torch.int32, torch.float64), (torch.int64, torch.float64)):
+        x = torch.arange(16, device=dev).to(dt)
+        assert wb.dwt(x, wt).dtype == out
+        assert wb.dwt(x, wavelet(WT.db2, WT.Lifting)).dtype == out
+    # row-major 2-D input is accepted (re-laid out), output is column-major with the same logical content
+    a = torch.randn(16, 8, device=dev, dtype=torch.float64)
+    y = wb.dwt(a, wt, 2)
+    ref = orc.dwt_filter(a.cpu().numpy(), wt.qmf, 2)
+    assert np.max(np.abs(to_np(y) - ref)) < 1e-13
+    # dwt!(y, x, filter, L)
+    yy = torch.empty_like(wb.colmajor(a))
+    wb.dwt_(yy, a, wt, 2)
+    assert torch.equal(yy, y)
+
+
+# ------------------------------------------------------------------------------------------------------
+# wavelet packets
+# ------------------------------------------------------------------------------------------------------
+def random_tree(n, r, p=0.6):
+    ns = wb.maxtransformlevels(n)
+    t = np.zeros(2 ** ns - 1, dtype=np.uint8)
+    t[0] = 1
+    for i in range(1, 2 ** (ns - 1)):
+        if t[i - 1]:
+            t[2 * i - 1] = r.random() < p
+            t[2 * i] = r.random() < p
+    assert wb.isvalidtree(n, t)
+    return t
+
+
+@pytest.mark.parametrize("n", [128, 40, 1024])
+def test_wpt_vs_oracle(dev, mode, n):
+    r = rng(14)
+    x = r.standard_normal(n)
+    xg = to_gpu(x, dev)
+    wf, wl = wavelet(WT.sym8 if n >= 128 else WT.db2), wavelet(WT.db2, WT.Lifting)
+    Lmax = wb.maxtransformlevels(n)
+    trees = [wb.maketree(n, L, "full") for L in range(0, Lmax + 1)]
+    trees += [wb.maketree(n, L, "dwt") for L in (1, Lmax)]
+    trees += [random_tree(n, r) for _ in range(4)]
+    for t in trees:
+        y = wb.wpt(xg, wf, t)
+        check(y, orc.wpt_filter(x, wf.qmf, t), mode, Lmax, 4.0)
+        check(wb.iwpt(y, wf, t), orc.wpt_filter(to_np(y), wf.qmf, t, fw=False), mode, Lmax, 4.0)
+        yl = wb.wpt(xg, wl, t)
+        check(yl, orc.wpt_lifting(x, wl.step, wl.norm1, wl.norm2, t), mode, 2 * Lmax, 8.0)
+        check(wb.iwpt(yl, wl, t), orc.wpt_lifting(to_np(yl), wl.step, wl.norm1, wl.norm2, t, fw=False), mode, 2 * Lmax, 8.0)
+    # integer L form and relations (test/transforms.jl:266-323)
+    assert torch.equal(wb.wpt(xg, wf, 1), wb.dwt(xg, wf, 1))
+    assert torch.equal(wb.wpt(xg, wf, wb.maketree(n, 2, "dwt")), wb.dwt(xg, wf, 2))
+    full = wb.wpt(xg, wf)
+    assert float((wb.iwpt(full, wf) - xg).abs().max()) < 1e-10
+
+
+def test_wpt_batch_and_inplace(dev, mode):
+    n, B = 256, 6
+    x = rng(15).standard_normal((n, B)).astype(np.float32)
+    wf = wavelet(WT.sym8)
+    y = to_np(wb.wpt(to_gpu(x, dev), wf))
+    t = wb.maketree(n, 8, "full")
+    for b in range(B):
+        check(np.ascontiguousarray(y[:, b]), orc.wpt_filter(x[:, b].copy(), wf.qmf, t), mode)
+    wl = wavelet(WT.cdf97, WT.Lifting)
+    z = to_gpu(x[:, 0].copy(), dev)
+    wb.wpt_(z, wl)
+    check(z, orc.wpt_lifting(x[:, 0].copy(), wl.step, wl.norm1, wl.norm2, t), mode)
+
+
+# ------------------------------------------------------------------------------------------------------
+# error behaviour (transforms_filter.jl:25-34, transforms_lifting.jl:131-140, test/transforms.jl:203-212)
+# ------------------------------------------------------------------------------------------------------
+def test_errors(dev):
+    wt, wl = wavelet(WT.db2), wavelet(WT.db2, WT.Lifting)
+    x = torch.randn(24, device=dev, dtype=torch.float64)
+    with pytest.raises(wb.ArgumentError, match="sufficient power of 2"):
+        wb.dwt(x, wt, 4)
+    with pytest.raises(wb.ArgumentError, match="L must be positive"):
+        wb.dwt(x, wt, -1)
+    with pytest.raises(wb.ArgumentError, match="in array is out array"):
+        wb.dwt_(x, x, wt, 1)
+    with pytest.raises(wb.DimensionMismatch):
+        wb.dwt_(torch.empty(12, device=dev, dtype=torch.float64), x, wt, 1)
+    with pytest.raises(wb.ArgumentError, match="square/cube"):
+        wb.dwt(torch.randn(8, 16, device=dev), wl, 1)
+    with pytest.raises(wb.ArgumentError, match="invalid tree"):
+        wb.wpt(x, wt, np.array([0, 1, 0, 0, 0, 0, 0], dtype=np.uint8))
+    with pytest.raises(TypeError):
+        wb.dwt(torch.randn(8), wt)                      # CPU tensor: no fallback
+    with pytest.raises(TypeError):
+        wavelet(WT.cdf97)                               # no CDF 9/7 filter pair
+
+
+# ------------------------------------------------------------------------------------------------------
+# C ABI details: caller workspace, streams, host-buffer entry points
+# ------------------------------------------------------------------------------------------------------
+def test_workspace_and_stream(dev):
+    import ctypes as C
+    from wavelets_b200 import _lib
+    L = _lib.lib()
+    wt = wavelet(WT.db4)
+    q = np.ascontiguousarray(wt.qmf)
+    n, B, lv = 4096, 16, 12
+    x = to_gpu(rng(16).standard_normal((n, B)), dev)
+    y = torch.empty_like(x)
+    dims = _lib.dims_array([n])
+    need = L.wb200_workspace_bytes(0, 1, dims, B, lv, _lib.F64, 0)
+    ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+    s = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(s):
+        rc = L.wb200_dwt_filter(y.data_ptr(), x.data_ptr(), 1, dims, B, q.ctypes.data_as(C.POINTER(C.c_double)), len(q),
+                                lv, 1, _lib.F64, ws.data_ptr(), need, C.c_void_p(s.cuda_stream), 0)
+    s.synchronize()
+    assert rc == 0
+    assert torch.equal(y, wb.dwtc(x, wt))
+    if need > 256:
+        rc = L.wb200_dwt_filter(y.data_ptr(), x.data_ptr(), 1, dims, B, q.ctypes.data_as(C.POINTER(C.c_double)), len(q),
+                                lv, 1, _lib.F64, ws.data_ptr(), 16, None, 0)
+        assert rc == _lib.EWORKSPACE
+
+
+def test_host_entry_points(dev):
+    import ctypes as C
+    from wavelets_b200 import _lib
+    L = _lib.lib()
+    wt = wavelet(WT.db4)
+    q = np.ascontiguousarray(wt.qmf)
+    n, B = 8192, 40
+    x = np.asfortranarray(rng(17).standard_normal((n, B)).astype(np.float32))
+    y = np.empty_like(x, order="F")
+    dims = _lib.dims_array([n])
+    rc = L.wb200_dwt_filter_host(y.ctypes.data, x.ctypes.data, 1, dims, B, q.ctypes.data_as(C.POINTER(C.c_double)),
+                                 len(q), 13, 1, _lib.F32, 0, 0)
+    assert rc == 0, L.wb200_last_error_string()
+    yd = to_np(wb.dwtc(to_gpu(x, dev), wt))
+    assert np.array_equal(y, yd)
+    wl = wavelet(WT.cdf97, WT.Lifting)
+    steps, ns = _lib.make_steps(wl)
+    img = np.asfortranarray(rng(18).standard_normal((128, 128, 3)).astype(np.float32))
+    out = np.empty_like(img, order="F")
+    rc = L.wb200_dwt_lifting_host(out.ctypes.data, img.ctypes.data, 2, _lib.dims_array([128, 128]), 3, steps, ns,
+                                  wl.norm1, wl.norm2, 5, 1, _lib.F32, 0, 0)
+    assert rc == 0, L.wb200_last_error_string()
+    assert np.array_equal(out, to_np(wb.dwtc(to_gpu(img, dev), wl, 5)))
+
+
+# ------------------------------------------------------------------------------------------------------
+# BASELINE-size properties (no full-size oracle run: size-independent invariants + oracle on a few columns)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_full_size_1d_db4(dev, dtype):
+    """config 2 shape: N = 2^20, db4, L = 20, a batch of columns."""
+    n, B = 1 << 20, 16
+    wt = wavelet(WT.db4)
+    g = torch.Generator(device=dev); g.manual_seed(42)
+    x = torch.randn((B, n), generator=g, device=dev, dtype=dtype).t()      # column-major (n, B)
+    y = wb.dwtc(x, wt)
+    xr = wb.idwtc(y, wt)
+    rt = float((xr - x).abs().max())
+    assert rt < (1e-10 if dtype == torch.float64 else 2e-4), rt
+    # orthogonality: energy is preserved
+    ex, ey = float((x.double() ** 2).sum()), float((y.double() ** 2).sum())
+    assert abs(ex - ey) / ex < (1e-12 if dtype == torch.float64 else 1e-5)
+    # linearity
+    x2 = torch.randn((B, n), generator=g, device=dev, dtype=dtype).t()
+    lin = (wb.dwtc(x + 2 * x2, wt) - (y + 2 * wb.dwtc(x2, wt))).abs().max()
+    assert float(lin) < (1e-11 if dtype == torch.float64 else 1e-3)
+    # oracle on two columns
+    for b in (0, B - 1):
+        ref = orc.dwt_filter(x[:, b].cpu().numpy().copy(), wt.qmf, 20)
+        d = float(np.max(np.abs(to_np(y[:, b]).astype(np.float64) - ref.astype(np.float64))))
+        assert d < (1e-11 if dtype == torch.float64 else 1e-4), d
+
+
+def test_full_size_2d_cdf97(dev):
+    """config 3 shape: 4096 x 4096 Float32, cdf97 lifting, L = 8."""
+    wl = wavelet(WT.cdf97, WT.Lifting)
+    g = torch.Generator(device=dev); g.manual_seed(42)
+    x = torch.randn((4096, 4096), generator=g, device=dev, dtype=torch.float32)
+    y = wb.dwt(x, wl, 8)
+    xr = wb.idwt(y, wl, 8)
+    assert float((xr - x).abs().max()) < 1e-4
+    # oracle on the same image (CPU, ~1 s)
+    ref = orc.dwt_lifting(wb.colmajor(x).cpu().numpy(), wl.step, wl.norm1, wl.norm2, 8)
+    assert float(np.max(np.abs(to_np(y) - ref))) < 2e-4
+    # Float64 round trip < 1e-10
+    xd = x[:1024, :1024].double()
+    assert float((wb.idwt(wb.dwt(xd, wl, 8), wl, 8) - wb.colmajor(xd)).abs().max()) < 1e-10

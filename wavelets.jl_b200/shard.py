@@ -1,0 +1,75 @@
+"""Batch sharding across the GPUs of one box.
+
+Every signal / image of a batch is an independent transform, so multi-GPU execution is a pure batch
+split: rank r owns a contiguous block of slices along the last (batch) dimension and runs the single-GPU
+path on it.  There is no data-path collective; NCCL is used only for the setup broadcast of the tiny
+wavelet descriptor (when rank 0 owns it), an optional gather of results and the scalar all-reduce that
+closes a timed region (bench.py).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+__all__ = ["shard_range", "shard_sizes", "broadcast_descriptor", "allreduce_max", "allreduce_sum", "gather_columns"]
+
+
+def shard_sizes(batch: int, world: int):
+    """Contiguous blocks of batch//world slices, the remainder going to the low ranks."""
+    q, r = divmod(int(batch), int(world))
+    return [q + (1 if i < r else 0) for i in range(world)]
+
+
+def shard_range(batch: int, rank: int, world: int) -> Tuple[int, int]:
+    sizes = shard_sizes(batch, world)
+    lo = sum(sizes[:rank])
+    return lo, lo + sizes[rank]
+
+
+def broadcast_descriptor(obj, src: int = 0):
+    """Broadcast a small picklable wavelet descriptor (qmf / step table) from `src` to every rank."""
+    import torch.distributed as dist
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def _allreduce(value: float, op, device):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=op)
+    return float(t.item())
+
+
+def allreduce_max(value: float, device="cpu") -> float:
+    import torch.distributed as dist
+    return _allreduce(value, dist.ReduceOp.MAX, device)
+
+
+def allreduce_sum(value: float, device="cpu") -> float:
+    import torch.distributed as dist
+    return _allreduce(value, dist.ReduceOp.SUM, device)
+
+
+def gather_columns(local, batch: int, dst: int = 0):
+    """Gather each rank's (n..., b_r) shard on `dst` and concatenate along the batch dimension (the inverse
+    of the split).  Shards may have different sizes; they travel as separate point-to-point messages."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    sizes = shard_sizes(batch, world)
+    if rank == dst:
+        parts = []
+        for r in range(world):
+            if r == dst:
+                parts.append(local.contiguous())
+            else:
+                shape = list(local.shape[:-1]) + [sizes[r]]
+                buf = torch.empty(shape, dtype=local.dtype, device=local.device)
+                if sizes[r]:
+                    dist.recv(buf, src=r)
+                parts.append(buf)
+        return torch.cat(parts, dim=-1)
+    if local.shape[-1]:
+        dist.send(local.contiguous(), dst=dst)
+    return None
