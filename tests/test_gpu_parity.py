@@ -349,10 +349,10 @@ def test_workspace_and_stream(dev):
     s.synchronize()
     assert rc == 0
     assert torch.equal(y, wb.dwtc(x, wt))
-    if need > 256:
-        rc = L.wb200_dwt_filter(y.data_ptr(), x.data_ptr(), 1, dims, B, q.ctypes.data_as(C.POINTER(C.c_double)), len(q),
-                                lv, 1, _lib.F64, ws.data_ptr(), 16, None, 0)
-        assert rc == _lib.EWORKSPACE
+    # a caller workspace that is too small is refused (generic per-level path: n/2 + n/4 scratch per column)
+    rc = L.wb200_dwt_filter(y.data_ptr(), x.data_ptr(), 1, dims, B, q.ctypes.data_as(C.POINTER(C.c_double)), len(q),
+                            lv, 1, _lib.F64, ws.data_ptr(), 16, None, _lib.FLAG_FORCE_GENERIC)
+    assert rc == _lib.EWORKSPACE
 
 
 def test_host_entry_points(dev):
@@ -422,3 +422,63 @@ def test_full_size_2d_cdf97(dev):
     # Float64 round trip < 1e-10
     xd = x[:1024, :1024].double()
     assert float((wb.idwt(wb.dwt(xd, wl, 8), wl, 8) - wb.colmajor(xd)).abs().max()) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused 1-D tile kernels (TMA-staged multi-level tiles + whole-line tail), forced at small sizes through the
+# tuning environment variables so that the oracle finishes in milliseconds
+# ------------------------------------------------------------------------------------------------------
+def _kernel_names():
+    import ctypes as C
+    from wavelets_b200 import _lib
+    buf = C.create_string_buffer(1 << 14)
+    nb = _lib.lib().wb200_profile_collect(buf, len(buf))
+    return {ln.split()[0] for ln in buf.raw[:nb].decode().splitlines()}
+
+
+@pytest.fixture
+def small_tiles(monkeypatch):
+    for k, v in {"WB200_TAILMAX_F32": "128", "WB200_TAILMAX_F64": "128", "WB200_TILE_F32": "256", "WB200_TILE_F64": "256"}.items():
+        monkeypatch.setenv(k, v)
+    yield
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("wname", ["haar", "db2", "db3", "db4", "db5", "db6", "db7", "sym8", "db9", "db10"])
+def test_fused_tiles_vs_oracle(dev, mode, small_tiles, dtype, wname):
+    from wavelets_b200 import _lib
+    wt = wavelet(wavelet_class(wname))
+    for n, B, L in ((2048, 3, 11), (2048, 1, 2), (3072, 2, 10), (8192, 2, 13), (1024, 5, 3), (512, 2, 1), (16384, 1, 14)):
+        x = rng(n + B + L).standard_normal((n, B)).astype(dtype)
+        _lib.lib().wb200_profile_enable(1)
+        y = wb.dwtc(to_gpu(x, dev), wt, L)
+        xr = wb.idwtc(y, wt, L)
+        _lib.lib().wb200_profile_enable(0)
+        names = _kernel_names()
+        if not (n == 3072 and len(wt) >= 18):    # 192-sample lines cannot host a 20-tap halo in a 64-sample tile: generic
+            assert {"fused_ana_tiles", "fused_syn_tiles"} <= names, names
+        check(y, orc.dwt_filter_batch(x, 1, wt.qmf, L), mode, L, 4.0)
+        check(xr, orc.dwt_filter_batch(to_np(y), 1, wt.qmf, L, fw=False), mode, L, 4.0)
+
+
+@pytest.mark.parametrize("kmax", [1, 2, 3, 8])
+@pytest.mark.parametrize("wname", ["db4", "db10", "haar"])
+def test_fused_tiles_stage_splits(dev, small_tiles, monkeypatch, kmax, wname):
+    """every split of the levels into tile stages (+ tail) gives the same bits (multi-stage chains included)"""
+    monkeypatch.setenv("WB200_KMAX", str(kmax))
+    from wavelets_b200 import _lib
+    wt = wavelet(wavelet_class(wname))
+    n, B = 8192, 2
+    for L in (13, 9, 4):
+        x = rng(kmax * 10 + L).standard_normal((n, B))
+        wb.set_strict_fp(True)
+        try:
+            _lib.lib().wb200_profile_enable(1)
+            y = wb.dwtc(to_gpu(x, dev), wt, L)
+            xr = wb.idwtc(y, wt, L)
+            _lib.lib().wb200_profile_enable(0)
+        finally:
+            wb.set_strict_fp(False)
+        assert {"fused_ana_tiles", "fused_syn_tiles"} <= _kernel_names()
+        assert np.array_equal(to_np(y), orc.dwt_filter_batch(x, 1, wt.qmf, L))
+        assert np.array_equal(to_np(xr), orc.dwt_filter_batch(to_np(y), 1, wt.qmf, L, fw=False))

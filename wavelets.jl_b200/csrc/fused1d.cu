@@ -1,9 +1,740 @@
-// fused1d.cu -- placeholder until the fused kernels land (generic passes handle everything).
+// fused1d.cu -- fused multi-level 1-D filter-bank DWT for batches of contiguous columns (sm_100a).
+//
+// One transform direction is at most two launches, however many levels it has:
+//
+//   forward   stage A  k_ana_tiles : a CTA stages TILE input samples (+ halo) of one column into shared memory
+//                                    with TMA bulk copies (cp.async.bulk + mbarrier; a second copy brings the
+//                                    periodic wrap), then runs K analysis levels back to back out of shared
+//                                    memory: every level's detail half goes straight to HBM with 64/128-bit
+//                                    coalesced stores, the shrinking approximation stays on chip.
+//             stage B  k_ana_tail  : the remaining n/2^K-sample approximation of a column fits one CTA's shared
+//                                    memory; one CTA finishes all remaining levels there.
+//   inverse   stage B' k_syn_tail  : levels L..K+1 of a column entirely in shared memory,
+//             stage A' k_syn_tiles : a CTA stages its slice of a_K and of d_K..d_1 (TMA bulk copies, wrap pieces
+//                                    included), synthesises K levels in shared memory and streams the TILE
+//                                    output samples with 128-bit stores.
+//
+// So HBM traffic is ~ (1 + halo/TILE + 2^-K) x the compulsory 2*sizeof(T) bytes per sample instead of the
+// 2x of a launch per level.  Decimation is fused with the filter; the detail band is produced
+// from the same register window as the approximation (d[k + F/2 - 1] and a[k] read the same F inputs).
+//
+// Arithmetic is the reference's (filtdown!/filtup! closed forms) in the reference's summation
+// order; STRICT keeps multiply and add separately rounded (bit-identical to the CPU path), otherwise FMA.
 #include "fused.cuh"
+
+#include <cstdlib>
+
 namespace wb {
+
+// ---------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy (global -> shared)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy: 16-byte aligned src/dst, size a multiple of 16
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// Copy `count` elements of the periodic line `line` (period n) starting at (possibly negative / overflowing)
+// index `lo` into dst.  lo, count and n are multiples of the 16-byte vector, count <= n.  Returns bytes issued.
 template <typename T>
-int32_t fused_dwt(const PassOp<T> &, T *, const T *, const ArrayGeom &, int, bool, void *, size_t, cudaStream_t, uint32_t) { return -1; }
-size_t fused_workspace_bytes(const ArrayGeom &, int, int, bool, bool, uint32_t) { return 0; }
+__device__ __forceinline__ uint32_t tma_load_wrapped(T *dst, const T *line, int64_t lo, int count, int64_t n, uint64_t *bar) {
+    if (lo < 0) lo += n;
+    if (lo >= n) lo -= n;
+    const int64_t first = (lo + count <= n) ? count : (n - lo);
+    tma_bulk_g2s(dst, line + lo, (uint32_t)(first * sizeof(T)), bar);
+    if (first < count) tma_bulk_g2s(dst + first, line, (uint32_t)((count - first) * sizeof(T)), bar);
+    return (uint32_t)(count * sizeof(T));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// small vector helpers (float4 / double2 granularity = 16 bytes)
+// ---------------------------------------------------------------------------------------------------
+template <typename T> struct Vec;
+template <> struct Vec<float> { using v16 = float4; using v8 = float2; static constexpr int N16 = 4; };
+template <> struct Vec<double> { using v16 = double2; static constexpr int N16 = 2; };
+
+template <int N> __device__ __forceinline__ void load_window(float (&w)[N], const float *p) {
+    static_assert(N % 2 == 0, "window must be even");
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < N / 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4 *>(p + 4 * i);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const float2 v = *reinterpret_cast<const float2 *>(p + 2 * i);
+            w[2 * i] = v.x; w[2 * i + 1] = v.y;
+        }
+    }
+}
+template <int N> __device__ __forceinline__ void load_window(double (&w)[N], const double *p) {
+    static_assert(N % 2 == 0, "window must be even");
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const double2 v = *reinterpret_cast<const double2 *>(p + 2 * i);
+        w[2 * i] = v.x; w[2 * i + 1] = v.y;
+    }
+}
+// 8-byte-aligned (float) / 16-byte-aligned (double) pair loads
+template <int N> __device__ __forceinline__ void load_pairs(float (&w)[N], const float *p) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const float2 v = *reinterpret_cast<const float2 *>(p + 2 * i);
+        w[2 * i] = v.x; w[2 * i + 1] = v.y;
+    }
+}
+template <int N> __device__ __forceinline__ void load_pairs(double (&w)[N], const double *p) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const double2 v = *reinterpret_cast<const double2 *>(p + 2 * i);
+        w[2 * i] = v.x; w[2 * i + 1] = v.y;
+    }
+}
+__device__ __forceinline__ void store2(float *p, float a, float b) { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store2(double *p, double a, double b) { *reinterpret_cast<double2 *>(p) = make_double2(a, b); }
+__device__ __forceinline__ void store4(float *p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ void store4(double *p, double a, double b, double c, double d) {
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+    *reinterpret_cast<double2 *>(p + 2) = make_double2(c, d);
+}
+// streaming (evict-first) global stores: outputs are written once and not re-read by this kernel
+__device__ __forceinline__ void gstore2(float *p, float a, float b) { __stcs(reinterpret_cast<float2 *>(p), make_float2(a, b)); }
+__device__ __forceinline__ void gstore2(double *p, double a, double b) { __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b)); }
+__device__ __forceinline__ void gstore4(float *p, float a, float b, float c, float d) {
+    __stcs(reinterpret_cast<float4 *>(p), make_float4(a, b, c, d));
+}
+__device__ __forceinline__ void gstore4(double *p, double a, double b, double c, double d) {
+    __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b));
+    __stcs(reinterpret_cast<double2 *>(p + 2), make_double2(c, d));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// compile-time geometry of one even-length filter
+// ---------------------------------------------------------------------------------------------------
+template <int F> struct FGeom {
+    static_assert(F % 2 == 0 && F >= 2, "fused kernels take even filter lengths");
+    static constexpr int Q = F / 2;
+    // analysis: the detail computed from the window starting at 2j + WO is d[j + DS]; DS even keeps pair stores aligned
+    static constexpr int DS = ((Q - 1) + 1) & ~1;
+    static constexpr int WO = 2 * DS - (F - 2);
+    static constexpr int WIN = F + 2 + WO;             // inputs per two output pairs (multiple of 4)
+    // synthesis: two output pairs (u, u+1) read a[u-QA .. u+2) and d[u .. u+QD)
+    static constexpr int QA = ((Q - 1) + 1) & ~1;
+    static constexpr int QD = ((Q + 1) + 1) & ~1;
+};
+
+template <typename T, int F> struct Taps {
+    T h[F];
+    T g[F];
+};
+
+constexpr int MAXK = 8; // fused levels per tile kernel
+
+// ===================================================================================================
+// FORWARD
+// ===================================================================================================
+struct AnaPlan {
+    int K;              // levels fused in stage A
+    int tile;           // input samples per CTA
+    int h0;             // staged halo samples (padded to a 16-byte multiple)
+    int NA[MAXK + 1];   // approximation samples computed at level l (index 0: staged inputs)
+    int ND[MAXK + 1];   // detail samples owned at level l
+};
+
+// one analysis level out of shared memory: `in` holds NAprev valid samples of a_{l-1}
+//   a[j]      = sum_m h[m]     in[2j + m]                 (increasing m)
+//   d[j + DS] = sum_p g[F-1-p] in[2j + WO + p]            (increasing input index)
+template <typename T, int F, bool STRICT, typename SA, typename SD>
+__device__ __forceinline__ void ana_level(const T *__restrict__ in, int NA, int ND, const Taps<T, F> &c, SA store_a, SD store_d) {
+    using fp = FP<STRICT>;
+    using G = FGeom<F>;
+    for (int p = 2 * threadIdx.x; p < NA; p += 2 * blockDim.x) {
+        T w[G::WIN];
+        load_window<G::WIN>(w, in + 2 * p);
+        T a0 = fp::mul(c.h[0], w[0]), a1 = fp::mul(c.h[0], w[2]);
+#pragma unroll
+        for (int m = 1; m < F; ++m) {
+            a0 = fp::mac(a0, c.h[m], w[m]);
+            a1 = fp::mac(a1, c.h[m], w[2 + m]);
+        }
+        store_a(p, a0, a1);
+        if (p < ND) {
+            T d0 = fp::mul(c.g[F - 1], w[G::WO]), d1 = fp::mul(c.g[F - 1], w[G::WO + 2]);
+#pragma unroll
+            for (int q = 1; q < F; ++q) {
+                d0 = fp::mac(d0, c.g[F - 1 - q], w[G::WO + q]);
+                d1 = fp::mac(d1, c.g[F - 1 - q], w[G::WO + 2 + q]);
+            }
+            store_d(p, d0, d1);
+        }
+    }
+}
+
+// Stage A.  The input line is a_{lvl0} of a column (src + col*src_stride, ncur = n0 >> lvl0 samples; lvl0 = 0: x).
+// Details of local level l go to the d_{lvl0+l} band of y (y + col*n0 + (n0 >> (lvl0+l))); the level-K
+// approximation goes to dst_a + col*dst_a_stride (y itself when no level remains, else the next stage's scratch).
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(256)
+k_ana_tiles(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, int64_t n0, int lvl0,
+            T *__restrict__ dst_a, int64_t dst_a_stride,
+            const __grid_constant__ Taps<T, F> c, const __grid_constant__ AnaPlan pl) {
+    using G = FGeom<F>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    T *bufA = reinterpret_cast<T *>(smem_raw + 128);
+    T *bufB = bufA + ((pl.tile + pl.h0 + 8 + 3) & ~3);
+    const int64_t col = blockIdx.y;
+    const int64_t s = (int64_t)blockIdx.x * pl.tile;
+    const int64_t ncur = n0 >> lvl0;
+    const T *xc = src + col * src_stride;
+    T *yc = y + col * n0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        const int count = pl.tile + pl.h0;
+        mbar_expect_tx(bar, (uint32_t)(count * sizeof(T)));
+        tma_load_wrapped<T>(bufA, xc, s, count, ncur, bar);
+    }
+    __syncthreads();       // barrier initialised before anyone polls it
+    mbar_wait(bar, 0);
+
+    const T *in = bufA;
+    T *out = bufB;
+    for (int l = 1; l <= pl.K; ++l) {
+        const int64_t nl = ncur >> l;              // length of the d band of this level (and of its approximation)
+        const int64_t sl = s >> l;
+        T *dband = yc + (n0 >> (lvl0 + l));        // d_j lives at y[n0/2^j .. n0/2^(j-1))
+        auto store_d = [&](int p, T d0, T d1) {
+            int64_t idx = sl + p + G::DS;
+            if (idx >= nl) idx -= nl;
+            gstore2(dband + idx, d0, d1);
+        };
+        if (l < pl.K) {
+            auto store_a = [&](int p, T a0, T a1) { store2(out + p, a0, a1); };
+            ana_level<T, F, STRICT>(in, pl.NA[l], pl.ND[l], c, store_a, store_d);
+            __syncthreads();
+            const T *t = in; in = out; out = const_cast<T *>(t);
+        } else {
+            T *dst = dst_a + col * dst_a_stride + sl;
+            auto store_a = [&](int p, T a0, T a1) { gstore2(dst + p, a0, a1); };
+            ana_level<T, F, STRICT>(in, pl.NA[l], pl.ND[l], c, store_a, store_d);
+        }
+    }
+}
+
+// whole-line tail: the CTA owns a column of length m (<= what fits), runs `levels` analysis levels in shared memory.
+// Scalar closed-form evaluation with periodic indexing (valid for any m_l >= 2, including m_l < F).
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(256)
+k_ana_tail(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, int64_t n, int m, int levels, int first_level,
+           const __grid_constant__ Taps<T, F> c) {
+    using fp = FP<STRICT>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *bufA = reinterpret_cast<T *>(smem_raw);
+    T *bufB = bufA + ((m + 3) & ~3);
+    const int64_t col = blockIdx.x;
+    const T *sc = src + col * src_stride;
+    T *yc = y + col * n;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) bufA[i] = sc[i];
+    __syncthreads();
+    T *in = bufA, *out = bufB;
+    int ml = m;
+    for (int l = 1; l <= levels; ++l) {
+        const int nh = ml >> 1;
+        const int lvl = first_level + l;             // absolute level number
+        T *dband = yc + (n >> lvl);
+        const bool last = (l == levels);
+        for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+            int ia = 2 * k;                          // < ml
+            T a = fp::mul(c.h[0], in[ia]);
+#pragma unroll
+            for (int q = 1; q < F; ++q) {
+                if (++ia == ml) ia = 0;
+                a = fp::mac(a, c.h[q], in[ia]);
+            }
+            int id = (2 * k + 2 - F) % ml;
+            if (id < 0) id += ml;
+            T d = fp::mul(c.g[F - 1], in[id]);
+#pragma unroll
+            for (int q = 1; q < F; ++q) {
+                if (++id == ml) id = 0;
+                d = fp::mac(d, c.g[F - 1 - q], in[id]);
+            }
+            dband[k] = d;
+            if (last) yc[k] = a; else out[k] = a;
+        }
+        __syncthreads();
+        T *t = in; in = out; out = t;
+        ml = nh;
+    }
+}
+
+// ===================================================================================================
+// INVERSE
+// ===================================================================================================
+struct SynPlan {
+    int K;                 // levels fused in stage A'
+    int tile;              // output samples per CTA
+    int rlo[MAXK + 1];     // a_l needed on [s_l + rlo[l], s_l + rhi[l])   (multiples of 4; rlo[0] = 0, rhi[0] = tile)
+    int rhi[MAXK + 1];
+    int dlo[MAXK + 1];     // d_l staged on [s_l + dlo[l], s_l + dhi[l])
+    int dhi[MAXK + 1];
+    int doff[MAXK + 1];    // element offset of the d_l stage inside shared memory
+    int aoff;              // element offset of the a_K stage
+    int poff, qoff;        // ping-pong buffers for a_{K-1} .. a_1
+};
+
+// one synthesis level: two output pairs per thread-iteration
+//   x[2u]   = (sum_{i=u-Q+1..u} h[2(u-i)]   a[i]) + (sum_{i=u..u+Q-1} g[2(i-u)+1] d[i])
+//   x[2u+1] = (sum_{i=u-Q+1..u} h[2(u-i)+1] a[i]) + (sum_{i=u..u+Q-1} g[2(i-u)]   d[i])
+// `abuf[i]` = a_l[s_l + rlo_l + i], `dbuf[i]` = d_l[s_l + dlo_l + i]; outputs a_{l-1}[s_{l-1} + rlo_{l-1} + 2*ur ...]
+template <typename T, int F, bool STRICT, typename SO>
+__device__ __forceinline__ void syn_level(const T *__restrict__ abuf, const T *__restrict__ dbuf, int oa, int od, int npairs,
+                                          const Taps<T, F> &c, SO store_out) {
+    using fp = FP<STRICT>;
+    using G = FGeom<F>;
+    constexpr int Q = G::Q;
+    for (int ur = 2 * threadIdx.x; ur < npairs; ur += 2 * blockDim.x) {
+        T wa[G::QA + 2], wd[G::QD];
+        load_pairs<G::QA + 2>(wa, abuf + oa + ur - G::QA);
+        load_pairs<G::QD>(wd, dbuf + od + ur);
+        T o[4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            // a[u' - k] = wa[QA + r - k], d[u' + k] = wd[r + k]
+            T rae = fp::mul(c.h[2 * (Q - 1)], wa[G::QA + r - (Q - 1)]);
+            T rao = fp::mul(c.h[2 * (Q - 1) + 1], wa[G::QA + r - (Q - 1)]);
+#pragma unroll
+            for (int k = Q - 2; k >= 0; --k) {
+                rae = fp::mac(rae, c.h[2 * k], wa[G::QA + r - k]);
+                rao = fp::mac(rao, c.h[2 * k + 1], wa[G::QA + r - k]);
+            }
+            T rde = fp::mul(c.g[1], wd[r]);
+            T rdo = fp::mul(c.g[0], wd[r]);
+#pragma unroll
+            for (int k = 1; k < Q; ++k) {
+                rde = fp::mac(rde, c.g[2 * k + 1], wd[r + k]);
+                rdo = fp::mac(rdo, c.g[2 * k], wd[r + k]);
+            }
+            o[2 * r] = fp::add(rae, rde);
+            o[2 * r + 1] = fp::add(rao, rdo);
+        }
+        store_out(ur, o[0], o[1], o[2], o[3]);
+    }
+}
+
+// Stage A'.  Produces a_{lvl0} of a column (ncur = n0 >> lvl0 samples, to dst + col*dst_stride: y when lvl0 == 0)
+// from a_{lvl0+K} (asrc + col*asrc_stride) and the detail bands d_{lvl0+K} .. d_{lvl0+1} of x.
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(256)
+k_syn_tiles(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restrict__ x, int64_t n0, int lvl0,
+            T *__restrict__ dst, int64_t dst_stride,
+            const __grid_constant__ Taps<T, F> c, const __grid_constant__ SynPlan pl) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    T *sm = reinterpret_cast<T *>(smem_raw + 128);
+    const int64_t col = blockIdx.y;
+    const int64_t s = (int64_t)blockIdx.x * pl.tile;
+    const int64_t ncur = n0 >> lvl0;
+    const T *xc = x + col * n0;
+    const int K = pl.K;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        uint32_t bytes = 0;
+        for (int l = 1; l <= K; ++l) bytes += (uint32_t)((pl.dhi[l] - pl.dlo[l]) * sizeof(T));
+        bytes += (uint32_t)((pl.rhi[K] - pl.rlo[K]) * sizeof(T));
+        mbar_expect_tx(bar, bytes);
+        tma_load_wrapped<T>(sm + pl.aoff, asrc + col * asrc_stride, (s >> K) + pl.rlo[K], pl.rhi[K] - pl.rlo[K], ncur >> K, bar);
+        for (int l = K; l >= 1; --l)
+            tma_load_wrapped<T>(sm + pl.doff[l], xc + (n0 >> (lvl0 + l)), (s >> l) + pl.dlo[l], pl.dhi[l] - pl.dlo[l], ncur >> l, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+
+    const T *abuf = sm + pl.aoff;
+    for (int l = K; l >= 1; --l) {
+        // produce the approximation one level up on [s_{l-1} + rlo[l-1], s_{l-1} + rhi[l-1])
+        const int npairs = (pl.rhi[l - 1] - pl.rlo[l - 1]) >> 1;           // output pairs = values of u
+        const int oa = (pl.rlo[l - 1] >> 1) - pl.rlo[l];                   // index of a[u_first] inside abuf
+        const int od = (pl.rlo[l - 1] >> 1) - pl.dlo[l];
+        const T *dbuf = sm + pl.doff[l];
+        if (l > 1) {
+            T *obuf = sm + (((l - 1) & 1) ? pl.poff : pl.qoff);
+            auto so = [&](int ur, T o0, T o1, T o2, T o3) { store4(obuf + 2 * ur, o0, o1, o2, o3); };
+            syn_level<T, F, STRICT>(abuf, dbuf, oa, od, npairs, c, so);
+            __syncthreads();
+            abuf = obuf;
+        } else {
+            T *o = dst + col * dst_stride + s;
+            auto so = [&](int ur, T o0, T o1, T o2, T o3) { gstore4(o + 2 * ur, o0, o1, o2, o3); };
+            syn_level<T, F, STRICT>(abuf, dbuf, oa, od, npairs, c, so);
+        }
+    }
+}
+
+// whole-line inverse tail: x[0:m) = [a_L | d_L | ... | d_{lv0+1}] of a column -> a_{lv0} (m samples)
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(256)
+k_syn_tail(const T *__restrict__ x, int64_t n, T *__restrict__ dst, int64_t dst_stride, int m, int levels,
+           const __grid_constant__ Taps<T, F> c) {
+    using fp = FP<STRICT>;
+    constexpr int Q = F / 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T *xin = reinterpret_cast<T *>(smem_raw);       // the m input coefficients
+    T *bufP = xin + ((m + 3) & ~3);                 // outputs of levels levels-2, levels-4, ... (<= m/2 samples)
+    T *bufQ = bufP + (((m >> 1) + 3) & ~3);         // outputs of levels levels-3, levels-5, ... (<= m/4 samples)
+    const int64_t col = blockIdx.x;
+    const T *xc = x + col * n;
+    T *dc = dst + col * dst_stride;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) xin[i] = xc[i];
+    __syncthreads();
+    int nh = m >> levels;                           // current approximation length
+    const T *a = xin;
+    for (int l = 0; l < levels; ++l) {
+        const T *d = xin + nh;                      // details of this level follow the coarser coefficients
+        const bool last = (l == levels - 1);
+        T *out = ((levels - 2 - l) & 1) ? bufQ : bufP;
+        for (int u = threadIdx.x; u < nh; u += blockDim.x) {
+            int ia = (u - (Q - 1)) % nh;
+            if (ia < 0) ia += nh;
+            T rae = fp::mul(c.h[2 * (Q - 1)], a[ia]);
+            T rao = fp::mul(c.h[2 * (Q - 1) + 1], a[ia]);
+#pragma unroll
+            for (int k = Q - 2; k >= 0; --k) {
+                if (++ia == nh) ia = 0;
+                rae = fp::mac(rae, c.h[2 * k], a[ia]);
+                rao = fp::mac(rao, c.h[2 * k + 1], a[ia]);
+            }
+            int id = u;
+            T rde = fp::mul(c.g[1], d[id]);
+            T rdo = fp::mul(c.g[0], d[id]);
+#pragma unroll
+            for (int k = 1; k < Q; ++k) {
+                if (++id == nh) id = 0;
+                rde = fp::mac(rde, c.g[2 * k + 1], d[id]);
+                rdo = fp::mac(rdo, c.g[2 * k], d[id]);
+            }
+            const T x0 = fp::add(rae, rde), x1 = fp::add(rao, rdo);
+            if (last) { dc[2 * u] = x0; dc[2 * u + 1] = x1; }
+            else      { out[2 * u] = x0; out[2 * u + 1] = x1; }
+        }
+        __syncthreads();
+        a = out;
+        nh <<= 1;
+    }
+}
+
+// ===================================================================================================
+// host side: planning and dispatch
+// ===================================================================================================
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+static inline int64_t pow2_factor(int64_t n) { return n & (-n); }
+
+// A transform of n samples / L levels is cut into tile stages (each fuses K_i levels out of shared-memory tiles,
+// reading a_{lv} from HBM once and writing its details + a_{lv+K_i}) followed by one whole-line tail stage for
+// the levels that remain once a column's approximation fits one CTA.
+struct Stage { int K, tile, lv0; };
+struct Fused1dCfg {
+    bool ok = false;
+    int nstages = 0;
+    Stage st[8];
+    int tail_levels = 0;   // levels left to the tail stage
+    int tail_lv0 = 0;      // levels done before the tail
+    int64_t m = 0;         // tail line length (n >> tail_lv0)
+};
+
+template <typename T> static int tail_max() { return sizeof(T) == 4 ? env_int("WB200_TAILMAX_F32", 16384) : env_int("WB200_TAILMAX_F64", 8192); }
+template <typename T> static int tile_max() { return sizeof(T) == 4 ? env_int("WB200_TILE_F32", 8192) : env_int("WB200_TILE_F64", 4096); }
+
+template <int F> static int ana_halo(int K, int (&H)[MAXK + 1]) {
+    using G = FGeom<F>;
+    H[K] = 0;
+    for (int l = K; l >= 1; --l) {
+        const int a = 2 * H[l] + F - 2, b = F - 2 + G::WO;
+        H[l - 1] = a > b ? a : b;
+    }
+    return H[0];
+}
+
+template <typename T, int F>
+static Fused1dCfg plan_split(int64_t n, int L) {
+    Fused1dCfg c;
+    const int tmax = tail_max<T>();
+    const int kcap = env_int("WB200_KMAX", MAXK);
+    const int halo_div = env_int("WB200_HALO_DIV", 4);        // accept at most tile/halo_div halo samples per tile
+    int64_t cur = n;
+    int lv = 0;
+    while (cur > tmax && lv < L) {
+        if (c.nstages == 8) return c;
+        int64_t tile = tile_max<T>();
+        const int64_t p2 = pow2_factor(cur);
+        while (tile > p2) tile >>= 1;                          // the tile must divide the line
+        while (tile > cur / 2) tile >>= 1;                     // at least two tiles per line (a wrap piece never overlaps its tile)
+        if (tile < 64 || (cur * (int64_t)sizeof(T)) % 16 != 0) return c;
+        int need = 0;
+        while ((cur >> need) > tmax) ++need;
+        int K = need < (L - lv) ? need : (L - lv);
+        if (K > kcap) K = kcap;
+        if (K > MAXK) K = MAXK;
+        int H[MAXK + 1];
+        while (K >= 1 && (ana_halo<F>(K, H) > tile / halo_div || (tile >> K) < 4)) --K;
+        if (K < 1) return c;
+        c.st[c.nstages++] = Stage{K, (int)tile, lv};
+        cur >>= K;
+        lv += K;
+    }
+    if (lv < L && cur > tmax) return c;                        // cannot happen (loop exits only when one is false)
+    c.tail_levels = L - lv;
+    c.tail_lv0 = lv;
+    c.m = cur;
+    c.ok = true;
+    return c;
+}
+
+template <int F> static void make_ana_plan(AnaPlan &pl, const Stage &sg, int vec) {
+    pl.K = sg.K; pl.tile = sg.tile;
+    int H[MAXK + 1];
+    ana_halo<F>(sg.K, H);
+    pl.h0 = (H[0] + vec - 1) / vec * vec;
+    pl.NA[0] = sg.tile + pl.h0; pl.ND[0] = sg.tile;
+    for (int l = 1; l <= sg.K; ++l) { pl.ND[l] = sg.tile >> l; pl.NA[l] = pl.ND[l] + H[l]; }
+}
+template <typename T> static size_t ana_smem(const AnaPlan &pl) {
+    const size_t a = ((size_t)pl.tile + pl.h0 + 8 + 3) & ~(size_t)3;
+    const size_t b = ((size_t)pl.NA[1] + 8 + 3) & ~(size_t)3;
+    return 128 + (a + b) * sizeof(T);
+}
+
+template <int F> static bool make_syn_plan(SynPlan &pl, const Stage &sg, int64_t ncur, size_t &smem_elems) {
+    using G = FGeom<F>;
+    auto dn4 = [](int v) { return (v >= 0) ? (v & ~3) : -(((-v) + 3) & ~3); };
+    auto up4 = [](int v) { return (v + 3) & ~3; };
+    pl.K = sg.K; pl.tile = sg.tile;
+    pl.rlo[0] = 0; pl.rhi[0] = sg.tile;
+    pl.dlo[0] = pl.dhi[0] = pl.doff[0] = 0;
+    for (int l = 1; l <= sg.K; ++l) {
+        pl.rlo[l] = dn4(pl.rlo[l - 1] / 2 - G::QA);   // rlo[l-1] is a multiple of 4, so /2 is exact
+        pl.rhi[l] = pl.rhi[l - 1] / 2;
+        pl.dlo[l] = dn4(pl.rlo[l - 1] / 2);
+        pl.dhi[l] = up4(pl.rhi[l - 1] / 2 + G::QD - 2);
+    }
+    size_t off = 0;
+    for (int l = 1; l <= sg.K; ++l) { pl.doff[l] = (int)off; off += (size_t)(pl.dhi[l] - pl.dlo[l]); }
+    pl.aoff = (int)off; off += (size_t)(pl.rhi[sg.K] - pl.rlo[sg.K]);
+    // ping-pong: poff holds the odd local levels a_1, a_3, ... ; qoff the even ones
+    size_t psz = 0, qsz = 0;
+    for (int l = 1; l < sg.K; ++l) {
+        const size_t sz = (size_t)(pl.rhi[l] - pl.rlo[l]);
+        if (l & 1) psz = sz > psz ? sz : psz; else qsz = sz > qsz ? sz : qsz;
+    }
+    pl.poff = (int)off; off += psz;
+    pl.qoff = (int)off; off += qsz;
+    smem_elems = off + 8;
+    // every staged range must fit inside its (periodic) band: a bulk copy wraps at most once
+    for (int l = 1; l <= sg.K; ++l)
+        if ((int64_t)(pl.dhi[l] - pl.dlo[l]) > (ncur >> l)) return false;
+    if ((int64_t)(pl.rhi[sg.K] - pl.rlo[sg.K]) > (ncur >> sg.K)) return false;
+    return true;
+}
+
+template <typename T, int F>
+static bool syn_plans_ok(const Fused1dCfg &cfg, int64_t n) {
+    for (int i = 0; i < cfg.nstages; ++i) {
+        SynPlan pl; size_t e;
+        if (!make_syn_plan<F>(pl, cfg.st[i], n >> cfg.st[i].lv0, e)) return false;
+        if (128 + e * sizeof(T) > 200 * 1024) return false;
+    }
+    return true;
+}
+
+// scratch layout: the approximation handed from stage i to the next stage (or to the tail) lives in buffer i & 1
+template <typename T>
+static size_t scratch_elems(const Fused1dCfg &cfg, int64_t n, int64_t B, size_t (&off)[2]) {
+    size_t sz[2] = {0, 0};
+    for (int i = 0; i < cfg.nstages; ++i) {
+        const int lv1 = cfg.st[i].lv0 + cfg.st[i].K;
+        const bool last_overall = (i == cfg.nstages - 1) && cfg.tail_levels == 0;
+        if (last_overall) continue;
+        const size_t e = (size_t)(n >> lv1) * (size_t)B;
+        if (e > sz[i & 1]) sz[i & 1] = e;
+    }
+    off[0] = 0;
+    off[1] = (sz[0] * sizeof(T) + 255) / 256 * 256 / sizeof(T);
+    return off[1] + sz[1];
+}
+
+template <typename T, int F, bool STRICT>
+static int32_t run_fused_1d(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t B, int L, bool fw,
+                            void *workspace, size_t ws_bytes, cudaStream_t st) {
+    const Fused1dCfg cfg = plan_split<T, F>(n, L);
+    if (!cfg.ok) return -1;
+    if (cfg.nstages > 0 && (B > 65535 || !syn_plans_ok<T, F>(cfg, n))) return -1;
+    Taps<T, F> taps;
+    for (int m = 0; m < F; ++m) { taps.h[m] = op.fc.h[m]; taps.g[m] = op.fc.g[m]; }
+
+    size_t soff[2];
+    const size_t scratch_bytes = scratch_elems<T>(cfg, n, B, soff) * sizeof(T);
+    T *scratch = nullptr;
+    bool own_scratch = false;
+    if (scratch_bytes) {
+        if (workspace != nullptr) {
+            if (ws_bytes < scratch_bytes) { set_error("workspace too small: %zu bytes given, %zu needed", ws_bytes, scratch_bytes); return WB200_EWORKSPACE; }
+            scratch = (T *)workspace;
+        } else {
+            if (cudaMallocAsync((void **)&scratch, scratch_bytes, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(fused scratch) failed"); return WB200_ECUDA; }
+            own_scratch = true;
+        }
+    }
+    int32_t rc = WB200_OK;
+    auto finish = [&]() { if (own_scratch) cudaFreeAsync(scratch, st); return rc; };
+    auto fail = [&](const char *what) { rc = WB200_ECUDA; set_error("%s", what); return finish(); };
+    // buffer holding the approximation after stage i (i = -1: the input itself)
+    auto abuf = [&](int i) -> T * { return scratch + soff[i & 1]; };
+
+    if (fw) {
+        for (int i = 0; i < cfg.nstages; ++i) {
+            const Stage &sg = cfg.st[i];
+            AnaPlan pl;
+            make_ana_plan<F>(pl, sg, 16 / (int)sizeof(T));
+            const size_t smem = ana_smem<T>(pl);
+            auto kern = k_ana_tiles<T, F, STRICT>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return fail("cudaFuncSetAttribute(k_ana_tiles) failed"); }
+            const int64_t ncur = n >> sg.lv0;
+            const T *src = (i == 0) ? x : abuf(i - 1);
+            const int64_t sstride = (i == 0) ? n : ncur;
+            const bool last_overall = (i == cfg.nstages - 1) && cfg.tail_levels == 0;
+            T *dsta = last_overall ? y : abuf(i);
+            const int64_t dstride = last_overall ? n : (ncur >> sg.K);
+            dim3 grid((unsigned)(ncur / sg.tile), (unsigned)B);
+            {
+                LaunchScope scope("fused_ana_tiles", st);
+                kern<<<grid, 256, smem, st>>>(src, sstride, y, n, sg.lv0, dsta, dstride, taps, pl);
+            }
+            if (!check_launch("fused_ana_tiles")) { rc = WB200_ECUDA; return finish(); }
+        }
+        if (cfg.tail_levels > 0) {
+            const int m = (int)cfg.m;
+            const size_t smem = ((size_t)((m + 3) & ~3) + (size_t)(((m >> 1) + 3) & ~3) + 8) * sizeof(T);
+            auto kern = k_ana_tail<T, F, STRICT>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return fail("cudaFuncSetAttribute(k_ana_tail) failed"); }
+            const T *src = cfg.nstages ? abuf(cfg.nstages - 1) : x;
+            const int64_t sstride = cfg.nstages ? cfg.m : n;
+            {
+                LaunchScope scope("fused_ana_tail", st);
+                kern<<<(unsigned)B, 256, smem, st>>>(src, sstride, y, n, m, cfg.tail_levels, cfg.tail_lv0, taps);
+            }
+            if (!check_launch("fused_ana_tail")) { rc = WB200_ECUDA; return finish(); }
+        }
+    } else {
+        if (cfg.tail_levels > 0) {
+            const int m = (int)cfg.m;
+            const size_t smem = ((size_t)((m + 3) & ~3) + (size_t)(((m >> 1) + 3) & ~3) + (size_t)(((m >> 2) + 3) & ~3) + 8) * sizeof(T);
+            auto kern = k_syn_tail<T, F, STRICT>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return fail("cudaFuncSetAttribute(k_syn_tail) failed"); }
+            T *dst = cfg.nstages ? abuf(cfg.nstages - 1) : y;
+            const int64_t dstride = cfg.nstages ? cfg.m : n;
+            {
+                LaunchScope scope("fused_syn_tail", st);
+                kern<<<(unsigned)B, 256, smem, st>>>(x, n, dst, dstride, m, cfg.tail_levels, taps);
+            }
+            if (!check_launch("fused_syn_tail")) { rc = WB200_ECUDA; return finish(); }
+        }
+        for (int i = cfg.nstages - 1; i >= 0; --i) {
+            const Stage &sg = cfg.st[i];
+            const int64_t ncur = n >> sg.lv0;
+            SynPlan pl; size_t elems;
+            if (!make_syn_plan<F>(pl, sg, ncur, elems)) return fail("internal: synthesis plan rejected after validation");
+            const size_t smem = 128 + elems * sizeof(T);
+            auto kern = k_syn_tiles<T, F, STRICT>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return fail("cudaFuncSetAttribute(k_syn_tiles) failed"); }
+            const bool last_overall = (i == cfg.nstages - 1) && cfg.tail_levels == 0;
+            const T *asrc = last_overall ? x : abuf(i);             // coarsest stage without a tail reads a_L from x
+            const int64_t astride = last_overall ? n : (ncur >> sg.K);
+            T *dst = (i == 0) ? y : abuf(i - 1);
+            const int64_t dstride = (i == 0) ? n : ncur;
+            dim3 grid((unsigned)(ncur / sg.tile), (unsigned)B);
+            {
+                LaunchScope scope("fused_syn_tiles", st);
+                kern<<<grid, 256, smem, st>>>(asrc, astride, x, n, sg.lv0, dst, dstride, taps, pl);
+            }
+            if (!check_launch("fused_syn_tiles")) { rc = WB200_ECUDA; return finish(); }
+        }
+    }
+    return finish();
+}
+
+template <typename T, bool STRICT>
+static int32_t dispatch_F(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t B, int L, bool fw,
+                          void *ws, size_t wsb, cudaStream_t st) {
+    switch (op.fc.F) {
+#define WB_CASE(FF) case FF: return run_fused_1d<T, FF, STRICT>(op, y, x, n, B, L, fw, ws, wsb, st);
+        WB_CASE(2) WB_CASE(4) WB_CASE(6) WB_CASE(8) WB_CASE(10) WB_CASE(12) WB_CASE(14) WB_CASE(16) WB_CASE(18) WB_CASE(20)
+#undef WB_CASE
+    default: return -1;
+    }
+}
+
+template <typename T>
+int32_t fused_dwt(const PassOp<T> &op, T *y, const T *x, const ArrayGeom &g, int L, bool fw,
+                  void *workspace, size_t ws_bytes, cudaStream_t st, uint32_t flags) {
+    (void)flags;
+    if (op.lifting || g.ndim != 1 || g.C != 1 || L < 1) return -1;
+    if (env_int("WB200_DISABLE_FUSED", 0)) return -1;
+    const int64_t n = g.dim[0];
+    if (((uintptr_t)x | (uintptr_t)y) & 15) return -1;
+    if ((n * (int64_t)sizeof(T)) % 16 != 0 && g.batch > 1) return -1;
+    if (op.strict) return dispatch_F<T, true>(op, y, x, n, g.batch, L, fw, workspace, ws_bytes, st);
+    return dispatch_F<T, false>(op, y, x, n, g.batch, L, fw, workspace, ws_bytes, st);
+}
+
+template <typename T> static size_t fused_ws_T(int64_t n, int64_t B, int L) {
+    // the split depends on the filter length only through the halo; take the worst case over the supported lengths
+    size_t need = 0;
+    auto one = [&](const Fused1dCfg &c) {
+        if (!c.ok) return;
+        size_t off[2];
+        const size_t b = scratch_elems<T>(c, n, B, off) * sizeof(T);
+        need = b > need ? b : need;
+    };
+    one(plan_split<T, 2>(n, L)); one(plan_split<T, 4>(n, L)); one(plan_split<T, 6>(n, L)); one(plan_split<T, 8>(n, L));
+    one(plan_split<T, 10>(n, L)); one(plan_split<T, 12>(n, L)); one(plan_split<T, 14>(n, L)); one(plan_split<T, 16>(n, L));
+    one(plan_split<T, 18>(n, L)); one(plan_split<T, 20>(n, L));
+    return need;
+}
+
+size_t fused_workspace_bytes(const ArrayGeom &g, int esize, int L, bool lifting, bool inplace, uint32_t flags) {
+    (void)inplace;
+    if (lifting || g.ndim != 1 || g.C != 1 || L < 1 || (flags & WB200_FLAG_FORCE_GENERIC)) return 0;
+    const size_t need = (esize == 4) ? fused_ws_T<float>(g.dim[0], g.batch, L) : fused_ws_T<double>(g.dim[0], g.batch, L);
+    return (need + 255) & ~(size_t)255;
+}
+
 template int32_t fused_dwt<float>(const PassOp<float> &, float *, const float *, const ArrayGeom &, int, bool, void *, size_t, cudaStream_t, uint32_t);
 template int32_t fused_dwt<double>(const PassOp<double> &, double *, const double *, const ArrayGeom &, int, bool, void *, size_t, cudaStream_t, uint32_t);
-}
+
+} // namespace wb
