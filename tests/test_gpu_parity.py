@@ -482,3 +482,32 @@ def test_fused_tiles_stage_splits(dev, small_tiles, monkeypatch, kmax, wname):
         assert {"fused_ana_tiles", "fused_syn_tiles"} <= _kernel_names()
         assert np.array_equal(to_np(y), orc.dwt_filter_batch(x, 1, wt.qmf, L))
         assert np.array_equal(to_np(xr), orc.dwt_filter_batch(to_np(y), 1, wt.qmf, L, fw=False))
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused 2-D lifting level kernels (tiles with register-resident lifting), vs the oracle
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("wname", ["cdf97", "haar", "db2"])
+@pytest.mark.parametrize("n,L,B", [(128, 1, 1), (256, 2, 1), (256, 8, 3), (512, 3, 2), (384, 2, 1)])
+def test_fused_lift2d_vs_oracle(dev, mode, dtype, wname, n, L, B):
+    from wavelets_b200 import _lib
+    wl = wavelet(getattr(WT, wname), WT.Lifting)
+    x = rng(n + L + B).standard_normal((n, n, B)).astype(dtype)
+    xg = to_gpu(x, dev)
+    _lib.lib().wb200_profile_enable(1)
+    y = wb.dwtc(xg, wl, L)
+    xr = wb.idwtc(y, wl, L)
+    _lib.lib().wb200_profile_enable(0)
+    names = _kernel_names()
+    if n % 128 == 0:
+        assert {"fused_lift2d_fwd", "fused_lift2d_inv"} <= names, names
+    ref = orc.dwt_lifting_batch(x, 2, wl.step, wl.norm1, wl.norm2, L)
+    check(y, ref, mode, 2 * L, 8.0)
+    check(xr, orc.dwt_lifting_batch(to_np(y), 2, wl.step, wl.norm1, wl.norm2, L, fw=False), mode, 2 * L, 8.0)
+    # in-place form on a single image
+    z = to_gpu(x[:, :, 0].copy(), dev)
+    wb.dwt_(z, wl, L)
+    check(z, np.asfortranarray(ref[:, :, 0]), mode, 2 * L, 8.0)
+    wb.idwt_(z, wl, L)
+    assert float(np.max(np.abs(to_np(z) - x[:, :, 0]))) < (1e-10 if dtype == np.float64 else 1e-4)

@@ -247,39 +247,45 @@ static int32_t run_1d(const PassOp<T> &op, T *y, const T *x, const ArrayGeom &g,
 // Buffers rotate src -> W1 (-> W2) -> y so that every pass is out of place; W1/W2 share the array layout.
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
-static int32_t run_nd(const PassOp<T> &op, T *y, const T *x, const ArrayGeom &g, int L, bool fw, Workspace &ws) {
+static int32_t run_nd(const PassOp<T> &op, T *y, const T *x, const ArrayGeom &g, int L, bool fw, Workspace &ws,
+                      int l_lo = 1, int l_hi = -1) {
+    // Processes levels l_lo..l_hi (forward: ascending, inverse: descending; default: all L levels).  A forward call
+    // with l_lo > 1 expects the level-(l_lo-1) approximation in y's leading corner; an inverse call with l_lo > 1
+    // leaves the level-(l_lo-1) approximation there (the fused kernels take over from it).
+    if (l_hi < 0) l_hi = L;
     const int nd = g.ndim;
+    // scratch arrays are compact: they only ever hold the corner of the largest processed level
+    ArrayGeom gw = g;
+    for (int a = 0; a < nd; ++a) gw.dim[a] = g.dim[a] >> (l_lo - 1);
     T *W[2] = {nullptr, nullptr};
     for (int q = 0; q < nd - 1; ++q) {
-        W[q] = (T *)ws.take(sizeof(T) * (size_t)g.total());
+        W[q] = (T *)ws.take(sizeof(T) * (size_t)gw.total());
         if (!W[q]) { set_error("internal: N-D workspace plan mismatch"); return WB200_EWORKSPACE; }
     }
-    for (int it = 0; it < L; ++it) {
-        const int l = fw ? it + 1 : L - it;
+    const int nlev = l_hi - l_lo + 1;
+    for (int it = 0; it < nlev; ++it) {
+        const int l = fw ? l_lo + it : l_hi - it;
         int64_t cor[3];
         for (int a = 0; a < 3; ++a) cor[a] = (a < nd) ? (g.dim[a] >> (l - 1)) : 1;
-        // buffer chain for this level
-        const T *src0 = (it == 0) ? x : y;
-        T *chain[4];
-        chain[0] = const_cast<T *>(src0);
-        for (int p = 1; p < nd; ++p) chain[p] = W[p - 1];
-        chain[nd] = y;
         for (int p = 0; p < nd; ++p) {
             const int ax = fw ? nd - p : p + 1;
             View<T> vs, vd; Extent e, e2; int64_t thr[4], thr2[4];
-            make_lines<T>(g, cor, ax, chain[p], vs, e, thr);
-            make_lines<T>(g, cor, ax, chain[p + 1], vd, e2, thr2);
-            const int64_t half = (cor[ax - 1] / 2) * vs.ls;
+            // source of this pass
+            if (p == 0) make_lines<T>(g, cor, ax, const_cast<T *>((fw && l > 1) ? y : x), vs, e, thr);
+            else        make_lines<T>(gw, cor, ax, W[p - 1], vs, e, thr);
+            // destination of this pass
+            if (p == nd - 1) make_lines<T>(g, cor, ax, y, vd, e2, thr2);
+            else             make_lines<T>(gw, cor, ax, W[p], vd, e2, thr2);
+            const int64_t nh = cor[ax - 1] / 2;
             if (fw) {
-                if (!op.analysis(cview(vs), vd, offset_view(vd, half), e)) return WB200_ECUDA;
+                if (!op.analysis(cview(vs), vd, offset_view(vd, nh * vd.ls), e)) return WB200_ECUDA;
             } else {
-                // first pass of an inverse level: the LL.. corner was produced by the previous level into y
-                const bool has_alt = (p == 0) && (it > 0);
+                // first pass of an inverse level: details (and, at level L, the approximation) come from x; below
+                // level L the LL.. corner was produced by the previous level into y
+                const bool has_alt = (p == 0) && (l < L);
                 View<T> valt; Extent e3; int64_t thr3[4];
                 make_lines<T>(g, cor, ax, y, valt, e3, thr3);
-                View<T> vsrc = vs;
-                if (p == 0) vsrc.p = const_cast<T *>(x); // details (and, at the coarsest level, the approximation) come from x
-                if (!op.synthesis(cview(vsrc), cview(offset_view(vsrc, half)), cview(valt), thr, has_alt, vd, e)) return WB200_ECUDA;
+                if (!op.synthesis(cview(vs), cview(offset_view(vs, nh * vs.ls)), cview(valt), thr, has_alt, vd, e)) return WB200_ECUDA;
             }
         }
     }
@@ -375,6 +381,22 @@ static size_t plan_dwt(const Call &c, int L, bool lifting, bool inplace, uint32_
     }
     return need;
 }
+// scratch of the generic N-D driver when it starts at level l_lo (compact corner buffers)
+static size_t plan_nd_from(const Call &c, int l_lo) {
+    const ArrayGeom &g = c.g;
+    size_t corner = (size_t)g.C * (size_t)g.batch;
+    for (int a = 0; a < g.ndim; ++a) corner *= (size_t)(g.dim[a] >> (l_lo - 1));
+    return (size_t)(g.ndim - 1) * align_up(corner * c.esize);
+}
+template <typename T>
+static size_t plan_fused2d(const PassOp<T> &op, const Call &c, int L, bool fw, bool inplace, int &Lf) {
+    Lf = fused2d_levels<T>(op, c.g, L, fw);
+    if (Lf == 0) return 0;
+    size_t need = align_up(fused2d_scratch_bytes<T>(c.g, Lf)) + 256;
+    if (inplace) need += align_up((size_t)c.g.total() * c.esize);
+    if (L > Lf) need += plan_nd_from(c, Lf + 1);
+    return need;
+}
 
 template <typename T>
 static int32_t dispatch_dwt(PassOp<T> &op, void *y, const void *x, const Call &c, int L, bool fw, bool lifting,
@@ -391,6 +413,44 @@ static int32_t dispatch_dwt(PassOp<T> &op, void *y, const void *x, const Call &c
     if (!(flags & WB200_FLAG_FORCE_GENERIC) && g.C == 1) {
         int32_t rc = fused_dwt<T>(op, (T *)y, (const T *)x, g, L, fw, workspace, ws_bytes, st, flags);
         if (rc >= 0) return rc;
+    }
+    // 2-D lifting: fused level kernels for the large levels, generic passes for the small remainder
+    if (!(flags & WB200_FLAG_FORCE_GENERIC) && g.C == 1 && g.ndim == 2 && lifting) {
+        int Lf = 0;
+        const size_t need = plan_fused2d<T>(op, c, L, fw, inplace, Lf);
+        if (Lf > 0) {
+            Workspace ws;
+            int32_t rc = ws.init(workspace, ws_bytes, need, st);
+            if (rc != WB200_OK) return rc;
+            void *scratch = ws.take(fused2d_scratch_bytes<T>(g, Lf) + 256);
+            const T *xin = (const T *)x;
+            if (inplace) { // the level kernels read x while other CTAs write y: stage a copy
+                T *x0 = (T *)ws.take(bytes);
+                if (!x0 || !scratch) { set_error("internal: fused 2-D workspace plan mismatch"); return WB200_EWORKSPACE; }
+                if (!cuda_ok(cudaMemcpyAsync(x0, x, bytes, cudaMemcpyDeviceToDevice, st), "cudaMemcpyAsync")) return WB200_ECUDA;
+                xin = x0;
+            }
+            const int64_t N = g.dim[0];
+            if (fw) {
+                rc = fused2d_run<T>(op, (T *)y, xin, nullptr, 0, 0, g, Lf, true, scratch, st);
+                if (rc != WB200_OK) return rc;
+                if (L > Lf) return run_nd<T>(op, (T *)y, (const T *)y, g, L, true, ws, Lf + 1, L);
+                return WB200_OK;
+            }
+            if (L <= Lf) return fused2d_run<T>(op, (T *)y, xin, xin, N, N * N, g, Lf, false, scratch, st);
+            rc = run_nd<T>(op, (T *)y, xin, g, L, false, ws, Lf + 1, L);
+            if (rc != WB200_OK) return rc;
+            if (Lf >= 2) // level Lf reads y's corner and writes scratch; y itself is only written by level 1, later
+                return fused2d_run<T>(op, (T *)y, xin, (const T *)y, N, N * N, g, Lf, false, scratch, st);
+            // Lf == 1: the single fused level would read y's corner while other CTAs overwrite y -> park the corner
+            const int64_t nf = N >> 1;
+            View<const T> vs; View<T> vd; Extent e;
+            e.len = nf; e.n[0] = 1; e.n[1] = nf; e.n[2] = 1; e.n[3] = g.batch;
+            vs.p = (const T *)y; vs.ls = 1; vs.s[0] = 0; vs.s[1] = N; vs.s[2] = 0; vs.s[3] = N * N;
+            vd.p = (T *)scratch; vd.ls = 1; vd.s[0] = 0; vd.s[1] = nf; vd.s[2] = 0; vd.s[3] = nf * nf;
+            if (!launch_copy_lines<T>(vs, vd, e, st)) return WB200_ECUDA;
+            return fused2d_run<T>(op, (T *)y, xin, (const T *)scratch, nf, nf * nf, g, Lf, false, scratch, st);
+        }
     }
     Workspace ws;
     int32_t rc = ws.init(workspace, ws_bytes, plan_dwt(c, L, lifting, inplace, flags | WB200_FLAG_FORCE_GENERIC), st);
@@ -611,6 +671,9 @@ extern "C" size_t wb200_workspace_bytes(int32_t kind, int32_t ndim, const int64_
     case 0: case 1: case 2: {
         size_t generic = plan_dwt(c, L, kind != 0, kind == 2, flags);
         size_t fused = fused_workspace_bytes(c.g, c.esize, L, kind != 0, kind == 2, flags);
+        // (the fused 2-D lifting path needs at most scratch (n^2/4 + n^2/16) + an in-place copy + the generic
+        //  remainder, which never exceeds the generic plan's full-size buffer plus the copy)
+        if (kind == 2 && c.g.ndim == 2) generic += align_up((size_t)c.g.total() * c.esize) + 1024;
         return generic > fused ? generic : fused;
     }
     case 3: case 4: {

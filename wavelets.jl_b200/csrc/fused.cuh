@@ -14,4 +14,17 @@ int32_t fused_dwt(const PassOp<T> &op, T *y, const T *x, const ArrayGeom &g, int
 // Device scratch the fused path needs for this shape (0 when it does not apply).
 size_t fused_workspace_bytes(const ArrayGeom &g, int esize, int L, bool lifting, bool inplace, uint32_t flags);
 
+// ---- 2-D lifting levels (fused2d.cu) ----------------------------------------------------------------------
+// Number of leading levels (1..Lf) the fused 2-D lifting kernels take for this call (0: none).
+template <typename T> int fused2d_levels(const PassOp<T> &op, const ArrayGeom &g, int L, bool fw);
+// Scratch for the approximation ping-pong of Lf fused levels.
+template <typename T> size_t fused2d_scratch_bytes(const ArrayGeom &g, int Lf);
+// forward: levels 1..Lf of x; detail quadrants land in y, the level-Lf approximation in y's leading corner.
+// inverse: levels Lf..1; the level-Lf approximation is read from ll_src (leading dimension ll_ld, batch stride
+// ll_bs: x's corner when no coarser level was inverted before, else where the generic remainder left it), details
+// from x; the result fills y.   x must not alias y; ll_src must not alias y when Lf == 1.
+template <typename T>
+int32_t fused2d_run(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int64_t ll_ld, int64_t ll_bs,
+                    const ArrayGeom &g, int Lf, bool fw, void *scratch, cudaStream_t st);
+
 } // namespace wb

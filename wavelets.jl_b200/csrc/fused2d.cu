@@ -1,0 +1,512 @@
+// fused2d.cu -- one-launch-per-level 2-D lifting transform (cdf 9/7, Haar, db2 schemes) for sm_100a.
+//
+// The reference's 2-D lifting level (src/Transforms/transforms_lifting.jl:158-191) makes, per line and per
+// dimension, a strided split pass, one pass per lifting step and a normalise/scatter pass -- its own KA GPU
+// extension launches 12 kernels per cdf97 level, with the dim-2 pass uncoalesced.  Here one CTA
+// stages a TI x TJ tile (+ the scheme's halo in both dimensions, periodic wrap folded into the load) in shared
+// memory, de-interleaved along dim 1 while loading, and runs
+//      forward:  dim-2 pass (rows)    -> dim-1 pass (columns) -> four coalesced quadrant stores
+//      inverse:  dim-1 pass (columns) -> dim-2 pass (rows)    -> one coalesced interleaved store
+// Each pass keeps a short segment of one line in REGISTERS and applies every predict/update step there (halo
+// pairs are recomputed per segment), so a sample costs one shared-memory read and one write per pass instead of
+// one per lifting step.  The shared row pitch is odd: the dim-2 pass walks rows with threads along dim 1
+// (stride 1), the dim-1 pass walks along a row with threads across rows (stride = odd pitch): both conflict-free.
+// A level therefore reads its input once and writes its output once: 2*sizeof(T) bytes per sample of the level.
+//
+// Arithmetic order is the reference's (lift_inbounds!/lift_perboundary!, normalize!): in
+// STRICT mode interior elements use x + ((c0*a + c1*b)), elements whose taps wrap use ((x + c0*a) + c1*b).
+#include "fused.cuh"
+
+#include <cstdlib>
+
+namespace wb {
+
+// ---------------------------------------------------------------------------------------------------
+// compile-time shapes of the lifting schemes the fused kernels specialise on (coefficients stay runtime)
+// ---------------------------------------------------------------------------------------------------
+#define WB_HD __host__ __device__ static constexpr
+struct ShapeCdf97F { // U@0[2], P@1[2], U@0[2], P@1[2]      (WT.SCHEMES "cdf9/7", forward order)
+    static constexpr int N = 4;
+    WB_HD int pred(int i) { return (i & 1); }
+    WB_HD int sh(int i) { return (i & 1); }
+    WB_HD int nc(int) { return 2; }
+};
+struct ShapeCdf97I { // reversed: P@1, U@0, P@1, U@0
+    static constexpr int N = 4;
+    WB_HD int pred(int i) { return !(i & 1); }
+    WB_HD int sh(int i) { return !(i & 1); }
+    WB_HD int nc(int) { return 2; }
+};
+struct ShapeHaarF { // P@0[1], U@0[1]
+    static constexpr int N = 2;
+    WB_HD int pred(int i) { return i == 0; }
+    WB_HD int sh(int) { return 0; }
+    WB_HD int nc(int) { return 1; }
+};
+struct ShapeHaarI { // U@0, P@0
+    static constexpr int N = 2;
+    WB_HD int pred(int i) { return i == 1; }
+    WB_HD int sh(int) { return 0; }
+    WB_HD int nc(int) { return 1; }
+};
+struct ShapeDb2F { // P@0[1], U@1[2], P@-1[1]
+    static constexpr int N = 3;
+    WB_HD int pred(int i) { return i != 1; }
+    WB_HD int sh(int i) { return i == 0 ? 0 : (i == 1 ? 1 : -1); }
+    WB_HD int nc(int i) { return i == 1 ? 2 : 1; }
+};
+struct ShapeDb2I { // P@-1, U@1, P@0
+    static constexpr int N = 3;
+    WB_HD int pred(int i) { return i != 1; }
+    WB_HD int sh(int i) { return i == 0 ? -1 : (i == 1 ? 1 : 0); }
+    WB_HD int nc(int i) { return i == 1 ? 2 : 1; }
+};
+template <class S> struct Halo {
+    WB_HD int left() { int h = 0; for (int i = 0; i < S::N; ++i) h += S::sh(i) > 0 ? S::sh(i) : 0; return h; }
+    WB_HD int right() { int h = 0; for (int i = 0; i < S::N; ++i) h += (S::nc(i) - 1 - S::sh(i)) > 0 ? (S::nc(i) - 1 - S::sh(i)) : 0; return h; }
+};
+#undef WB_HD
+
+template <class S, typename T> static bool shape_matches(const LiftScheme<T> &sc) {
+    if (sc.nsteps != S::N) return false;
+    for (int i = 0; i < S::N; ++i)
+        if ((sc.is_predict[i] != 0) != (S::pred(i) != 0) || sc.shift[i] != S::sh(i) || sc.nc[i] != S::nc(i)) return false;
+    return true;
+}
+
+// coefficients of one direction, trimmed to what the fused shapes need
+template <typename T> struct LiftCoefs {
+    T c[4][2];
+    T n1, n2;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// all lifting steps of one line segment, in registers.  s[p], d[p] are the polyphase pair p of the segment;
+// element 0 is global pair g0 (mod half).  Valid ranges shrink by each step's reach; the caller only consumes
+// pairs [HL, NP-HR).
+// ---------------------------------------------------------------------------------------------------
+template <typename T, class S, bool STRICT, int NP>
+__device__ __forceinline__ void lift_regs(T (&s)[NP], T (&d)[NP], const LiftCoefs<T> &lc, int g0, int half, bool edge) {
+    using fp = FP<STRICT>;
+    int lo_s = 0, hi_s = NP, lo_d = 0, hi_d = NP;
+#pragma unroll
+    for (int st = 0; st < S::N; ++st) {
+        const int sh = S::sh(st), nc = S::nc(st);
+        const bool pred = S::pred(st) != 0;
+        const int left = sh > 0 ? sh : 0, right = (nc - 1 - sh) > 0 ? (nc - 1 - sh) : 0;
+        int lo, hi;
+        if (pred) { lo = lo_s > lo_d + left ? lo_s : lo_d + left; hi = hi_s < hi_d - right ? hi_s : hi_d - right; lo_s = lo; hi_s = hi; }
+        else      { lo = lo_d > lo_s + left ? lo_d : lo_s + left; hi = hi_d < hi_s - right ? hi_d : hi_s - right; lo_d = lo; hi_d = hi; }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            if (p >= lo && p < hi) {
+                T v = pred ? s[p] : d[p];
+                // tap indices are compile-time constants after unrolling; the clamps only silence dead-code bounds
+                const int i0 = (p - sh) < 0 ? 0 : ((p - sh) >= NP ? NP - 1 : (p - sh));
+                const int i1 = (p + 1 - sh) < 0 ? 0 : ((p + 1 - sh) >= NP ? NP - 1 : (p + 1 - sh));
+                const T t0 = pred ? d[i0] : s[i0];
+                const T t1 = (nc > 1) ? (pred ? d[i1] : s[i1]) : T(0);
+                if (nc == 1) {
+                    v = fp::mac(v, lc.c[st][0], t0);
+                } else if (STRICT) {
+                    bool interior = true;
+                    if (edge) {
+                        int gi = g0 + p;
+                        if (gi < 0) gi += half; else if (gi >= half) gi -= half;
+                        interior = (gi >= left) && (gi <= half + sh - nc);
+                    }
+                    if (interior) v = fp::add(v, fp::mac(fp::mul(lc.c[st][0], t0), lc.c[st][1], t1));
+                    else          v = fp::mac(fp::mac(v, lc.c[st][0], t0), lc.c[st][1], t1);
+                } else {
+                    v = fp::mac(fp::mac(v, lc.c[st][0], t0), lc.c[st][1], t1);
+                }
+                if (pred) s[p] = v; else d[p] = v;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tile configuration
+// ---------------------------------------------------------------------------------------------------
+template <class S, int TI_, int TJ_, int SI_, int SJ_> struct Cfg2d {
+    static constexpr int TI = TI_, TJ = TJ_, SI = SI_, SJ = SJ_;
+    static constexpr int HL = Halo<S>::left(), HR = Halo<S>::right();
+    static constexpr int TIp = TI / 2, TJp = TJ / 2;
+    static constexpr int CP = TIp + HL + HR;          // staged pairs along dim 1
+    static constexpr int RJ = TJ + 2 * (HL + HR);     // staged rows (dim 2 samples)
+    static constexpr int P = CP | 1;                  // odd pitch
+    static constexpr int NPI = SI + HL + HR, NPJ = SJ + HL + HR;
+    static constexpr int ROW_TASKS_F = 2 * CP * (TJp / SJ);   // forward dim-2 pass: every staged column pair
+    static constexpr int COL_TASKS_F = TJ * (TIp / SI);       // forward dim-1 pass: owned rows only
+    static constexpr int COL_TASKS_I = RJ * (TIp / SI);       // inverse dim-1 pass: every staged row
+    static constexpr int ROW_TASKS_I = 2 * TIp * (TJp / SJ);  // inverse dim-2 pass: owned column pairs only
+    static constexpr int MAXT = ROW_TASKS_F > COL_TASKS_I ? (ROW_TASKS_F > COL_TASKS_F ? ROW_TASKS_F : COL_TASKS_F)
+                                                          : (COL_TASKS_I > ROW_TASKS_I ? COL_TASKS_I : ROW_TASKS_I);
+    static constexpr int NT = (MAXT + 31) / 32 * 32;
+    static_assert(TIp % SI == 0 && TJp % SJ == 0, "segments must tile the tile");
+};
+
+__device__ __forceinline__ int wrapi(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }
+
+// one element, global -> shared, asynchronously (LDGSTS)
+template <typename T> __device__ __forceinline__ void cp_async(T *dst_smem, const T *src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    if constexpr (sizeof(T) == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+    else                          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward level: src (n x n corner, leading dimension ld_s) -> LL to `ll`, the three detail quadrants to `yd`
+// ---------------------------------------------------------------------------------------------------
+template <typename T, class S, bool STRICT, class C>
+__global__ void __launch_bounds__(C::NT)
+k_lift2d_fwd(const T *__restrict__ src, int64_t ld_s, int64_t bs_s, T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll,
+             T *__restrict__ yd, int64_t ld_y, int64_t bs_y, int n, const __grid_constant__ LiftCoefs<T> lc) {
+    using fp = FP<STRICT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *Se = reinterpret_cast<T *>(smem_raw);
+    T *So = Se + C::RJ * C::P;
+    const int nh = n >> 1;
+    const int ip0 = blockIdx.x * C::TIp, j0 = blockIdx.y * C::TJ;
+    const int64_t b = blockIdx.z;
+    const T *sb = src + b * bs_s;
+    const int tid = threadIdx.x;
+
+    // ---- stage the tile with asynchronous copies (LDGSTS: global -> shared without a register round trip, so every
+    //      thread keeps all of its copies in flight).  Even and odd dim-1 samples go to separate arrays
+    //      (the polyphase split of the lifting scheme, fused into the load).
+    {
+        constexpr int TOT = C::RJ * C::CP;
+        for (int idx = tid; idx < TOT; idx += C::NT) {
+            const int r = idx / C::CP, c = idx - r * C::CP;
+            const int ipg = wrapi(ip0 - C::HL + c, nh);
+            const int j = wrapi(j0 - 2 * C::HL + r, n);
+            const T *p = sb + (int64_t)j * ld_s + 2 * ipg;
+            cp_async<T>(&Se[r * C::P + c], p);
+            cp_async<T>(&So[r * C::P + c], p + 1);
+        }
+        cp_async_wait_all();
+    }
+    __syncthreads();
+
+    // ---- dim-2 pass (the reference's "rows"): lines run across the staged rows, one thread per (column pair, parity, segment)
+    {
+        T s[C::NPJ], d[C::NPJ];
+        const bool act = tid < C::ROW_TASKS_F;
+        int c = 0, q = 0;
+        T *A = Se;
+        if (act) {
+            c = tid % C::CP;
+            const int rest = tid / C::CP;
+            A = (rest & 1) ? So : Se;
+            q = rest >> 1;
+#pragma unroll
+            for (int pp = 0; pp < C::NPJ; ++pp) {
+                s[pp] = A[(2 * (q * C::SJ + pp)) * C::P + c];
+                d[pp] = A[(2 * (q * C::SJ + pp) + 1) * C::P + c];
+            }
+        }
+        __syncthreads();
+        if (act) {
+            const int jp0 = (j0 >> 1) - C::HL + q * C::SJ;
+            const bool edge = STRICT && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1);
+            lift_regs<T, S, STRICT, C::NPJ>(s, d, lc, wrapi(jp0, nh), nh, edge);
+#pragma unroll
+            for (int pp = C::HL; pp < C::HL + C::SJ; ++pp) {
+                A[(2 * (q * C::SJ + pp)) * C::P + c] = fp::mul(s[pp], lc.n1);
+                A[(2 * (q * C::SJ + pp) + 1) * C::P + c] = fp::mul(d[pp], lc.n2);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- dim-1 pass ("columns"): lines run along a staged row, one thread per (owned row, segment) ----
+    {
+        T s[C::NPI], d[C::NPI];
+        const bool act = tid < C::COL_TASKS_F;
+        int r = 0, q = 0;
+        if (act) {
+            r = 2 * C::HL + tid % C::TJ;
+            q = tid / C::TJ;
+#pragma unroll
+            for (int pp = 0; pp < C::NPI; ++pp) {
+                s[pp] = Se[r * C::P + q * C::SI + pp];
+                d[pp] = So[r * C::P + q * C::SI + pp];
+            }
+        }
+        __syncthreads();
+        if (act) {
+            const bool edge = STRICT && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+            lift_regs<T, S, STRICT, C::NPI>(s, d, lc, wrapi(ip0 - C::HL + q * C::SI, nh), nh, edge);
+#pragma unroll
+            for (int pp = C::HL; pp < C::HL + C::SI; ++pp) {
+                Se[r * C::P + q * C::SI + pp] = fp::mul(s[pp], lc.n1);
+                So[r * C::P + q * C::SI + pp] = fp::mul(d[pp], lc.n2);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- stores: (s_i, s_j) -> LL, the other three combinations -> their quadrants of y ----
+    T *llb = ll + b * bs_ll;
+    T *yb = yd + b * bs_y;
+    for (int idx = tid; idx < 2 * C::TJ * C::TIp; idx += C::NT) {
+        const int ipl = idx % C::TIp;
+        const int rest = idx / C::TIp;
+        const int pi = rest & 1;
+        const int rr = rest >> 1;                  // owned row 0..TJ-1
+        const int j = j0 + rr;
+        const int jq = j >> 1, pj = j & 1;
+        const T v = (pi ? So : Se)[(2 * C::HL + rr) * C::P + C::HL + ipl];
+        if ((pi | pj) == 0) llb[(int64_t)jq * ld_ll + ip0 + ipl] = v;
+        else                yb[(int64_t)(pj * nh + jq) * ld_y + pi * nh + ip0 + ipl] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// inverse level: LL from `ll`, detail quadrants from `xd` -> dst (n x n, interleaved)
+// ---------------------------------------------------------------------------------------------------
+template <typename T, class S, bool STRICT, class C>
+__global__ void __launch_bounds__(C::NT)
+k_lift2d_inv(const T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll, const T *__restrict__ xd, int64_t ld_x, int64_t bs_x,
+             T *__restrict__ dst, int64_t ld_d, int64_t bs_d, int n, const __grid_constant__ LiftCoefs<T> lc) {
+    using fp = FP<STRICT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *Se = reinterpret_cast<T *>(smem_raw);
+    T *So = Se + C::RJ * C::P;
+    const int nh = n >> 1;
+    const int ip0 = blockIdx.x * C::TIp, j0 = blockIdx.y * C::TJ;
+    const int64_t b = blockIdx.z;
+    const T *llb = ll + b * bs_ll;
+    const T *xb = xd + b * bs_x;
+    const int tid = threadIdx.x;
+
+    // ---- stage (asynchronous copies): row r is output column j = j0 - 2HL + r, i.e. band pj = j&1 at index j>>1
+    {
+        constexpr int TOT = 2 * C::RJ * C::CP;
+        for (int idx = tid; idx < TOT; idx += C::NT) {
+            const int c = idx % C::CP;
+            const int rest = idx / C::CP;
+            const int pi = rest & 1;
+            const int r = rest >> 1;
+            const int ipg = wrapi(ip0 - C::HL + c, nh);
+            const int j = wrapi(j0 - 2 * C::HL + r, n);
+            const int jq = j >> 1, pj = j & 1;
+            const T *p = ((pi | pj) == 0) ? (llb + (int64_t)jq * ld_ll + ipg)
+                                          : (xb + (int64_t)(pj * nh + jq) * ld_x + pi * nh + ipg);
+            cp_async<T>(&(pi ? So : Se)[r * C::P + c], p);
+        }
+        cp_async_wait_all();
+    }
+    __syncthreads();
+    // ---- dim-1 pass first (inverse order), on every staged row ----
+    {
+        T s[C::NPI], d[C::NPI];
+        const bool act = tid < C::COL_TASKS_I;
+        int r = 0, q = 0;
+        if (act) {
+            r = tid % C::RJ;
+            q = tid / C::RJ;
+#pragma unroll
+            for (int pp = 0; pp < C::NPI; ++pp) {
+                s[pp] = fp::mul(Se[r * C::P + q * C::SI + pp], lc.n1);   // normalize! (reciprocal norms) precedes the steps
+                d[pp] = fp::mul(So[r * C::P + q * C::SI + pp], lc.n2);
+            }
+        }
+        __syncthreads();
+        if (act) {
+            const bool edge = STRICT && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+            lift_regs<T, S, STRICT, C::NPI>(s, d, lc, wrapi(ip0 - C::HL + q * C::SI, nh), nh, edge);
+#pragma unroll
+            for (int pp = C::HL; pp < C::HL + C::SI; ++pp) {
+                Se[r * C::P + q * C::SI + pp] = s[pp];
+                So[r * C::P + q * C::SI + pp] = d[pp];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- dim-2 pass on the owned column pairs ----
+    {
+        T s[C::NPJ], d[C::NPJ];
+        const bool act = tid < C::ROW_TASKS_I;
+        int c = 0, q = 0;
+        T *A = Se;
+        if (act) {
+            c = C::HL + tid % C::TIp;
+            const int rest = tid / C::TIp;
+            A = (rest & 1) ? So : Se;
+            q = rest >> 1;
+#pragma unroll
+            for (int pp = 0; pp < C::NPJ; ++pp) {
+                s[pp] = fp::mul(A[(2 * (q * C::SJ + pp)) * C::P + c], lc.n1);
+                d[pp] = fp::mul(A[(2 * (q * C::SJ + pp) + 1) * C::P + c], lc.n2);
+            }
+        }
+        __syncthreads();
+        if (act) {
+            const int jp0 = (j0 >> 1) - C::HL + q * C::SJ;
+            const bool edge = STRICT && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1);
+            lift_regs<T, S, STRICT, C::NPJ>(s, d, lc, wrapi(jp0, nh), nh, edge);
+#pragma unroll
+            for (int pp = C::HL; pp < C::HL + C::SJ; ++pp) {
+                A[(2 * (q * C::SJ + pp)) * C::P + c] = s[pp];
+                A[(2 * (q * C::SJ + pp) + 1) * C::P + c] = d[pp];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- merged store: out[2ip + {0,1}, j] = (Se, So)[row j][ip] ----
+    T *db = dst + b * bs_d;
+    for (int idx = tid; idx < C::TJ * C::TIp; idx += C::NT) {
+        const int ipl = idx % C::TIp;
+        const int rr = idx / C::TIp;
+        const int r = 2 * C::HL + rr;
+        const T v0 = Se[r * C::P + C::HL + ipl], v1 = So[r * C::P + C::HL + ipl];
+        T *p = db + (int64_t)(j0 + rr) * ld_d + 2 * (ip0 + ipl);
+        if constexpr (sizeof(T) == 4) *reinterpret_cast<float2 *>(p) = make_float2(v0, v1);
+        else                          *reinterpret_cast<double2 *>(p) = make_double2(v0, v1);
+    }
+}
+
+// ===================================================================================================
+// host side
+// ===================================================================================================
+static int env_int2(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+template <typename T> static void fill_coefs(LiftCoefs<T> &lc, const LiftScheme<T> &sc) {
+    for (int i = 0; i < 4; ++i)
+        for (int k = 0; k < 2; ++k) lc.c[i][k] = (i < sc.nsteps && k < sc.nc[i]) ? sc.coef[i][k] : T(0);
+    lc.n1 = sc.norm1; lc.n2 = sc.norm2;
+}
+
+template <typename T> struct Tile2d { static constexpr int TI = 128, TJ = 64; };
+
+template <class S, typename T> using CfgFor = Cfg2d<S, Tile2d<T>::TI, Tile2d<T>::TJ, 16, 16>;
+
+// 0: not a fused shape; 1: cdf97; 2: haar; 3: db2 (direction is implied by the scheme order)
+template <typename T> static int shape_id(const LiftScheme<T> &sc, bool fw) {
+    if (fw) {
+        if (shape_matches<ShapeCdf97F>(sc)) return 1;
+        if (shape_matches<ShapeHaarF>(sc)) return 2;
+        if (shape_matches<ShapeDb2F>(sc)) return 3;
+    } else {
+        if (shape_matches<ShapeCdf97I>(sc)) return 1;
+        if (shape_matches<ShapeHaarI>(sc)) return 2;
+        if (shape_matches<ShapeDb2I>(sc)) return 3;
+    }
+    return 0;
+}
+
+template <typename T>
+int fused2d_levels(const PassOp<T> &op, const ArrayGeom &g, int L, bool fw) {
+    if (!op.lifting || g.ndim != 2 || g.C != 1 || g.dim[0] != g.dim[1]) return 0;
+    if (env_int2("WB200_DISABLE_FUSED2D", 0)) return 0;
+    if (shape_id<T>(op.sc, fw) == 0) return 0;
+    if (g.batch > 65535) return 0;
+    const int tmax = Tile2d<T>::TI > Tile2d<T>::TJ ? Tile2d<T>::TI : Tile2d<T>::TJ;
+    int Lf = 0;
+    int64_t n = g.dim[0];
+    if (n > (int64_t)1 << 30) return 0;
+    while (Lf < L && n >= tmax && n % Tile2d<T>::TI == 0 && n % Tile2d<T>::TJ == 0) { ++Lf; n >>= 1; }
+    return Lf;
+}
+
+template <typename T> size_t fused2d_scratch_bytes(const ArrayGeom &g, int Lf) {
+    // approximation ping-pong: LL_1 (n/2)^2 in buffer 0, LL_2 (n/4)^2 in buffer 1, ... (the last fused level writes y)
+    if (Lf < 1) return 0;
+    const size_t n = (size_t)g.dim[0];
+    size_t b0 = (n / 2) * (n / 2) * (size_t)g.batch * sizeof(T);
+    size_t b1 = (Lf >= 3) ? (n / 4) * (n / 4) * (size_t)g.batch * sizeof(T) : 0;
+    return ((b0 + 255) & ~(size_t)255) + ((b1 + 255) & ~(size_t)255);
+}
+
+template <typename T, class S, bool STRICT, bool FW>
+static int32_t launch_level(const T *a, int64_t lda, int64_t bsa, const T *xd, int64_t ldx, int64_t bsx,
+                            T *o1, int64_t ld1, int64_t bs1, T *o2, int64_t ld2, int64_t bs2,
+                            int n, int64_t B, const LiftCoefs<T> &lc, cudaStream_t st) {
+    using C = CfgFor<S, T>;
+    const size_t smem = (size_t)2 * C::RJ * C::P * sizeof(T);
+    dim3 grid((unsigned)(n / C::TI), (unsigned)(n / C::TJ), (unsigned)B);
+    if constexpr (FW) {
+        auto kern = k_lift2d_fwd<T, S, STRICT, C>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaFuncSetAttribute(k_lift2d_fwd) failed"); return WB200_ECUDA; }
+        LaunchScope scope("fused_lift2d_fwd", st);
+        kern<<<grid, C::NT, smem, st>>>(a, lda, bsa, o1, ld1, bs1, o2, ld2, bs2, n, lc);
+    } else {
+        auto kern = k_lift2d_inv<T, S, STRICT, C>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaFuncSetAttribute(k_lift2d_inv) failed"); return WB200_ECUDA; }
+        LaunchScope scope("fused_lift2d_inv", st);
+        kern<<<grid, C::NT, smem, st>>>(a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, n, lc);
+    }
+    return check_launch(FW ? "fused_lift2d_fwd" : "fused_lift2d_inv") ? WB200_OK : WB200_ECUDA;
+}
+
+template <typename T, class SF, class SI_, bool STRICT>
+static int32_t run2d(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int64_t ll_ld, int64_t ll_bs,
+                     const ArrayGeom &g, int Lf, bool fw, void *scratch, cudaStream_t st) {
+    const int64_t N = g.dim[0], B = g.batch;
+    const int64_t bsN = N * N;
+    LiftCoefs<T> lc;
+    fill_coefs<T>(lc, op.sc);
+    T *buf[2];
+    buf[0] = (T *)scratch;
+    const size_t b0 = (((size_t)(N / 2) * (N / 2) * B * sizeof(T)) + 255) & ~(size_t)255;
+    buf[1] = (T *)((char *)scratch + b0);
+    // approximation of level l (1 <= l < Lf) lives compactly in buf[(l-1)&1] with leading dimension N>>l
+    if (fw) {
+        for (int l = 1; l <= Lf; ++l) {
+            const int n = (int)(N >> (l - 1));
+            const T *src = (l == 1) ? x : buf[(l - 2) & 1];
+            const int64_t lds = (l == 1) ? N : n, bss = (l == 1) ? bsN : (int64_t)n * n;
+            T *llo; int64_t ldl, bsl;
+            if (l == Lf) { llo = y; ldl = N; bsl = bsN; }                       // final approximation: y's corner
+            else         { llo = buf[(l - 1) & 1]; ldl = n / 2; bsl = (int64_t)(n / 2) * (n / 2); }
+            int32_t rc = launch_level<T, SF, STRICT, true>(src, lds, bss, nullptr, 0, 0, llo, ldl, bsl, y, N, bsN, n, B, lc, st);
+            if (rc != WB200_OK) return rc;
+        }
+    } else {
+        for (int l = Lf; l >= 1; --l) {
+            const int n = (int)(N >> (l - 1));
+            const T *lls; int64_t ldl, bsl;
+            if (l == Lf) { lls = ll_src; ldl = ll_ld; bsl = ll_bs; }            // x / y corner, or a parked compact copy
+            else         { lls = buf[(l - 1) & 1]; ldl = n / 2; bsl = (int64_t)(n / 2) * (n / 2); }
+            T *dst; int64_t ldd, bsd;
+            if (l == 1) { dst = y; ldd = N; bsd = bsN; }
+            else        { dst = buf[(l - 2) & 1]; ldd = n; bsd = (int64_t)n * n; }
+            int32_t rc = launch_level<T, SI_, STRICT, false>(lls, ldl, bsl, x, N, bsN, dst, ldd, bsd, nullptr, 0, 0, n, B, lc, st);
+            if (rc != WB200_OK) return rc;
+        }
+    }
+    return WB200_OK;
+}
+
+template <typename T>
+int32_t fused2d_run(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int64_t ll_ld, int64_t ll_bs,
+                    const ArrayGeom &g, int Lf, bool fw, void *scratch, cudaStream_t st) {
+    const int id = shape_id<T>(op.sc, fw);
+#define WB_RUN(SF, SI_)                                                                                            \
+    return op.strict ? run2d<T, SF, SI_, true>(op, y, x, ll_src, ll_ld, ll_bs, g, Lf, fw, scratch, st)              \
+                     : run2d<T, SF, SI_, false>(op, y, x, ll_src, ll_ld, ll_bs, g, Lf, fw, scratch, st)
+    switch (id) {
+    case 1: WB_RUN(ShapeCdf97F, ShapeCdf97I);
+    case 2: WB_RUN(ShapeHaarF, ShapeHaarI);
+    case 3: WB_RUN(ShapeDb2F, ShapeDb2I);
+    default: return -1;
+    }
+#undef WB_RUN
+}
+
+#define WB_INST(T)                                                                                                 \
+    template int fused2d_levels<T>(const PassOp<T> &, const ArrayGeom &, int, bool);                                \
+    template size_t fused2d_scratch_bytes<T>(const ArrayGeom &, int);                                               \
+    template int32_t fused2d_run<T>(const PassOp<T> &, T *, const T *, const T *, int64_t, int64_t, const ArrayGeom &, int, bool, void *, cudaStream_t);
+WB_INST(float)
+WB_INST(double)
+#undef WB_INST
+
+} // namespace wb
