@@ -177,17 +177,26 @@ k_lift2d_fwd(const T *__restrict__ src, int64_t ld_s, int64_t bs_s, T *__restric
     const int tid = threadIdx.x;
 
     // ---- stage the tile with asynchronous copies (LDGSTS: global -> shared without a register round trip, so every
-    //      thread keeps all of its copies in flight).  Even and odd dim-1 samples go to separate arrays
-    //      (the polyphase split of the lifting scheme, fused into the load).
+    //      thread keeps all of its copies in flight).  Even and odd dim-1 samples go to separate arrays (the
+    //      polyphase split of the lifting scheme, fused into the load).  A thread owns one column pair and walks
+    //      down the rows with incremental addressing.
     {
-        constexpr int TOT = C::RJ * C::CP;
-        for (int idx = tid; idx < TOT; idx += C::NT) {
-            const int r = idx / C::CP, c = idx - r * C::CP;
+        constexpr int RT = C::NT / C::CP;                   // rows covered per sweep
+        const int c = tid % C::CP, rsub = tid / C::CP;
+        if (rsub < RT) {
             const int ipg = wrapi(ip0 - C::HL + c, nh);
-            const int j = wrapi(j0 - 2 * C::HL + r, n);
+            int j = wrapi(j0 - 2 * C::HL + rsub, n);
             const T *p = sb + (int64_t)j * ld_s + 2 * ipg;
-            cp_async<T>(&Se[r * C::P + c], p);
-            cp_async<T>(&So[r * C::P + c], p + 1);
+            T *se = Se + rsub * C::P + c, *so = So + rsub * C::P + c;
+            const int64_t pstep = (int64_t)RT * ld_s, pwrap = (int64_t)n * ld_s;
+#pragma unroll 6
+            for (int r = rsub; r < C::RJ; r += RT) {
+                cp_async<T>(se, p);
+                cp_async<T>(so, p + 1);
+                se += RT * C::P; so += RT * C::P;
+                j += RT; p += pstep;
+                if (j >= n) { j -= n; p -= pwrap; }
+            }
         }
         cp_async_wait_all();
     }
@@ -249,19 +258,27 @@ k_lift2d_fwd(const T *__restrict__ src, int64_t ld_s, int64_t bs_s, T *__restric
         }
         __syncthreads();
     }
-    // ---- stores: (s_i, s_j) -> LL, the other three combinations -> their quadrants of y ----
-    T *llb = ll + b * bs_ll;
-    T *yb = yd + b * bs_y;
-    for (int idx = tid; idx < 2 * C::TJ * C::TIp; idx += C::NT) {
-        const int ipl = idx % C::TIp;
-        const int rest = idx / C::TIp;
-        const int pi = rest & 1;
-        const int rr = rest >> 1;                  // owned row 0..TJ-1
-        const int j = j0 + rr;
-        const int jq = j >> 1, pj = j & 1;
-        const T v = (pi ? So : Se)[(2 * C::HL + rr) * C::P + C::HL + ipl];
-        if ((pi | pj) == 0) llb[(int64_t)jq * ld_ll + ip0 + ipl] = v;
-        else                yb[(int64_t)(pj * nh + jq) * ld_y + pi * nh + ip0 + ipl] = v;
+    // ---- stores: (s_i, s_j) -> LL, the other three combinations -> their quadrants of y.  A thread owns one
+    //      (dim-1 pair, dim-1 parity, dim-2 parity) and walks the tile's dim-2 pairs: 128-byte coalesced rows.
+    {
+        T *llb = ll + b * bs_ll;
+        T *yb = yd + b * bs_y;
+        const int ipl = tid % C::TIp;
+        const int rest = tid / C::TIp;
+        if (rest < 4) {
+            const int pi = rest & 1, pj = rest >> 1;
+            const int jq0 = j0 >> 1;
+            const T *srcp = (pi ? So : Se) + (2 * C::HL + pj) * C::P + C::HL + ipl;
+            T *dp; int64_t dstep;
+            if ((pi | pj) == 0) { dp = llb + (int64_t)jq0 * ld_ll + ip0 + ipl; dstep = ld_ll; }
+            else                { dp = yb + (int64_t)(pj * nh + jq0) * ld_y + pi * nh + ip0 + ipl; dstep = ld_y; }
+#pragma unroll 8
+            for (int k = 0; k < C::TJp; ++k) {
+                *dp = *srcp;
+                srcp += 2 * C::P;
+                dp += dstep;
+            }
+        }
     }
 }
 
@@ -283,20 +300,30 @@ k_lift2d_inv(const T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll, const T *__
     const T *xb = xd + b * bs_x;
     const int tid = threadIdx.x;
 
-    // ---- stage (asynchronous copies): row r is output column j = j0 - 2HL + r, i.e. band pj = j&1 at index j>>1
+    // ---- stage (asynchronous copies): staged row r is output column j = j0 - 2HL + r, i.e. band pj = j & 1 at
+    //      index jq = j >> 1.  A thread owns one dim-1 pair and one dim-2 parity and walks the dim-2 pairs.
     {
-        constexpr int TOT = 2 * C::RJ * C::CP;
-        for (int idx = tid; idx < TOT; idx += C::NT) {
-            const int c = idx % C::CP;
-            const int rest = idx / C::CP;
-            const int pi = rest & 1;
-            const int r = rest >> 1;
+        constexpr int RT = (C::NT / C::CP) & ~1;            // even, so that a thread keeps its dim-2 parity
+        const int c = tid % C::CP, rsub = tid / C::CP;
+        if (rsub < RT) {
             const int ipg = wrapi(ip0 - C::HL + c, nh);
-            const int j = wrapi(j0 - 2 * C::HL + r, n);
-            const int jq = j >> 1, pj = j & 1;
-            const T *p = ((pi | pj) == 0) ? (llb + (int64_t)jq * ld_ll + ipg)
-                                          : (xb + (int64_t)(pj * nh + jq) * ld_x + pi * nh + ipg);
-            cp_async<T>(&(pi ? So : Se)[r * C::P + c], p);
+            const int j = wrapi(j0 - 2 * C::HL + rsub, n);
+            int jq = j >> 1;
+            const int pj = j & 1;
+            const T *pe, *po;
+            int64_t estep, ostep;
+            if (pj == 0) { pe = llb + (int64_t)jq * ld_ll + ipg; estep = ld_ll; }
+            else         { pe = xb + (int64_t)(nh + jq) * ld_x + ipg; estep = ld_x; }
+            po = xb + (int64_t)(pj * nh + jq) * ld_x + nh + ipg; ostep = ld_x;
+            T *se = Se + rsub * C::P + c, *so = So + rsub * C::P + c;
+#pragma unroll 6
+            for (int r = rsub; r < C::RJ; r += RT) {
+                cp_async<T>(se, pe);
+                cp_async<T>(so, po);
+                se += RT * C::P; so += RT * C::P;
+                jq += RT / 2; pe += (RT / 2) * estep; po += (RT / 2) * ostep;
+                if (jq >= nh) { jq -= nh; pe -= (int64_t)nh * estep; po -= (int64_t)nh * ostep; }
+            }
         }
         cp_async_wait_all();
     }
@@ -357,16 +384,23 @@ k_lift2d_inv(const T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll, const T *__
         }
         __syncthreads();
     }
-    // ---- merged store: out[2ip + {0,1}, j] = (Se, So)[row j][ip] ----
-    T *db = dst + b * bs_d;
-    for (int idx = tid; idx < C::TJ * C::TIp; idx += C::NT) {
-        const int ipl = idx % C::TIp;
-        const int rr = idx / C::TIp;
-        const int r = 2 * C::HL + rr;
-        const T v0 = Se[r * C::P + C::HL + ipl], v1 = So[r * C::P + C::HL + ipl];
-        T *p = db + (int64_t)(j0 + rr) * ld_d + 2 * (ip0 + ipl);
-        if constexpr (sizeof(T) == 4) *reinterpret_cast<float2 *>(p) = make_float2(v0, v1);
-        else                          *reinterpret_cast<double2 *>(p) = make_double2(v0, v1);
+    // ---- merged store: out[2ip + {0,1}, j] = (Se, So)[row j][ip]; a thread owns one dim-1 pair and walks the rows
+    {
+        T *db = dst + b * bs_d;
+        constexpr int RS = C::NT / C::TIp;
+        const int ipl = tid % C::TIp, rsub = tid / C::TIp;
+        if (rsub < RS) {
+            const T *pe = Se + (2 * C::HL + rsub) * C::P + C::HL + ipl;
+            const T *po = So + (2 * C::HL + rsub) * C::P + C::HL + ipl;
+            T *p = db + (int64_t)(j0 + rsub) * ld_d + 2 * (ip0 + ipl);
+            const int64_t pstep = (int64_t)RS * ld_d;
+#pragma unroll 4
+            for (int rr = rsub; rr < C::TJ; rr += RS) {
+                if constexpr (sizeof(T) == 4) *reinterpret_cast<float2 *>(p) = make_float2(*pe, *po);
+                else                          *reinterpret_cast<double2 *>(p) = make_double2(*pe, *po);
+                pe += RS * C::P; po += RS * C::P; p += pstep;
+            }
+        }
     }
 }
 
