@@ -275,7 +275,8 @@ def main():
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+            per_col = tj.get(args.dtype, {}).get(dom, {}).get("dram_bytes_per_column")
+            traffic = per_col * B if per_col else None          # ncu --set full capture, scaled to this batch
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": dom, "launches": cnt, "kernel_ms_total": ms,

@@ -132,13 +132,19 @@ __device__ __forceinline__ void gstore4(double *p, double a, double b, double c,
 // ---------------------------------------------------------------------------------------------------
 // compile-time geometry of one even-length filter
 // ---------------------------------------------------------------------------------------------------
-template <int F> struct FGeom {
+// PA = output pairs per thread-iteration of the analysis level: 2 for 4-byte samples (16-byte window loads at
+// 16-byte thread stride), 1 for 8-byte samples (two pairs would put the 16-byte loads at a 32-byte thread stride:
+// a 2-way shared-memory bank conflict, measured at 129 M conflicts per launch in profiles/r01_fused1d_f64.md).
+template <typename T> struct AnaPairs { static constexpr int value = sizeof(T) == 4 ? 2 : 1; };
+
+template <int F, int PA = 2> struct FGeom {
     static_assert(F % 2 == 0 && F >= 2, "fused kernels take even filter lengths");
     static constexpr int Q = F / 2;
-    // analysis: the detail computed from the window starting at 2j + WO is d[j + DS]; DS even keeps pair stores aligned
-    static constexpr int DS = ((Q - 1) + 1) & ~1;
+    // analysis: the detail computed from the window starting at 2j + WO is d[j + DS]; DS a multiple of PA keeps the
+    // PA-wide detail stores aligned
+    static constexpr int DS = PA == 2 ? (((Q - 1) + 1) & ~1) : (Q - 1);
     static constexpr int WO = 2 * DS - (F - 2);
-    static constexpr int WIN = F + 2 + WO;             // inputs per two output pairs (multiple of 4)
+    static constexpr int WIN = F + 2 * (PA - 1) + WO;  // inputs per thread-iteration (PA = 2: a multiple of 4)
     // synthesis: two output pairs (u, u+1) read a[u-QA .. u+2) and d[u .. u+QD)
     static constexpr int QA = ((Q - 1) + 1) & ~1;
     static constexpr int QD = ((Q + 1) + 1) & ~1;
@@ -168,25 +174,28 @@ struct AnaPlan {
 template <typename T, int F, bool STRICT, typename SA, typename SD>
 __device__ __forceinline__ void ana_level(const T *__restrict__ in, int NA, int ND, const Taps<T, F> &c, SA store_a, SD store_d) {
     using fp = FP<STRICT>;
-    using G = FGeom<F>;
-    for (int p = 2 * threadIdx.x; p < NA; p += 2 * blockDim.x) {
+    constexpr int PA = AnaPairs<T>::value;
+    using G = FGeom<F, PA>;
+    for (int p = PA * threadIdx.x; p < NA; p += PA * blockDim.x) {
         T w[G::WIN];
         load_window<G::WIN>(w, in + 2 * p);
-        T a0 = fp::mul(c.h[0], w[0]), a1 = fp::mul(c.h[0], w[2]);
+        T a[PA];
 #pragma unroll
-        for (int m = 1; m < F; ++m) {
-            a0 = fp::mac(a0, c.h[m], w[m]);
-            a1 = fp::mac(a1, c.h[m], w[2 + m]);
-        }
-        store_a(p, a0, a1);
+        for (int r = 0; r < PA; ++r) a[r] = fp::mul(c.h[0], w[2 * r]);
+#pragma unroll
+        for (int m = 1; m < F; ++m)
+#pragma unroll
+            for (int r = 0; r < PA; ++r) a[r] = fp::mac(a[r], c.h[m], w[2 * r + m]);
+        store_a(p, a);
         if (p < ND) {
-            T d0 = fp::mul(c.g[F - 1], w[G::WO]), d1 = fp::mul(c.g[F - 1], w[G::WO + 2]);
+            T d[PA];
 #pragma unroll
-            for (int q = 1; q < F; ++q) {
-                d0 = fp::mac(d0, c.g[F - 1 - q], w[G::WO + q]);
-                d1 = fp::mac(d1, c.g[F - 1 - q], w[G::WO + 2 + q]);
-            }
-            store_d(p, d0, d1);
+            for (int r = 0; r < PA; ++r) d[r] = fp::mul(c.g[F - 1], w[G::WO + 2 * r]);
+#pragma unroll
+            for (int q = 1; q < F; ++q)
+#pragma unroll
+                for (int r = 0; r < PA; ++r) d[r] = fp::mac(d[r], c.g[F - 1 - q], w[G::WO + 2 * r + q]);
+            store_d(p, d);
         }
     }
 }
@@ -199,7 +208,8 @@ __global__ void __launch_bounds__(256)
 k_ana_tiles(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, int64_t n0, int lvl0,
             T *__restrict__ dst_a, int64_t dst_a_stride,
             const __grid_constant__ Taps<T, F> c, const __grid_constant__ AnaPlan pl) {
-    using G = FGeom<F>;
+    constexpr int PA = AnaPairs<T>::value;
+    using G = FGeom<F, PA>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     T *bufA = reinterpret_cast<T *>(smem_raw + 128);
@@ -224,20 +234,28 @@ k_ana_tiles(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, in
     for (int l = 1; l <= pl.K; ++l) {
         const int64_t nl = ncur >> l;              // length of the d band of this level (and of its approximation)
         const int64_t sl = s >> l;
-        T *dband = yc + (n0 >> (lvl0 + l));        // d_j lives at y[n0/2^j .. n0/2^(j-1))
-        auto store_d = [&](int p, T d0, T d1) {
-            int64_t idx = sl + p + G::DS;
-            if (idx >= nl) idx -= nl;
-            gstore2(dband + idx, d0, d1);
+        // d_j lives at y[n0/2^j .. n0/2^(j-1)); this tile's details start DS further (same register window as the
+        // approximation) and wrap to the band start in the line's last tile: 32-bit tile-relative addressing
+        T *dbase = yc + (n0 >> (lvl0 + l)) + sl + G::DS;
+        const int64_t room = nl - sl - G::DS;                      // pairs before the wrap
+        const int wrap_at = room < (int64_t)pl.ND[l] ? (int)room : 0x7fffffff;
+        const int wrap_by = (int)(nl < 0x7fffffff ? nl : 0);
+        auto store_d = [&](int p, const T (&d)[PA]) {
+            T *q = dbase + (p >= wrap_at ? p - wrap_by : p);
+            if constexpr (PA == 2) gstore2(q, d[0], d[1]); else __stcs(q, d[0]);
         };
         if (l < pl.K) {
-            auto store_a = [&](int p, T a0, T a1) { store2(out + p, a0, a1); };
+            auto store_a = [&](int p, const T (&a)[PA]) {
+                if constexpr (PA == 2) store2(out + p, a[0], a[1]); else out[p] = a[0];
+            };
             ana_level<T, F, STRICT>(in, pl.NA[l], pl.ND[l], c, store_a, store_d);
             __syncthreads();
             const T *t = in; in = out; out = const_cast<T *>(t);
         } else {
             T *dst = dst_a + col * dst_a_stride + sl;
-            auto store_a = [&](int p, T a0, T a1) { gstore2(dst + p, a0, a1); };
+            auto store_a = [&](int p, const T (&a)[PA]) {
+                if constexpr (PA == 2) gstore2(dst + p, a[0], a[1]); else __stcs(dst + p, a[0]);
+            };
             ana_level<T, F, STRICT>(in, pl.NA[l], pl.ND[l], c, store_a, store_d);
         }
     }
@@ -471,8 +489,8 @@ struct Fused1dCfg {
 template <typename T> static int tail_max() { return sizeof(T) == 4 ? env_int("WB200_TAILMAX_F32", 16384) : env_int("WB200_TAILMAX_F64", 8192); }
 template <typename T> static int tile_max() { return sizeof(T) == 4 ? env_int("WB200_TILE_F32", 8192) : env_int("WB200_TILE_F64", 4096); }
 
-template <int F> static int ana_halo(int K, int (&H)[MAXK + 1]) {
-    using G = FGeom<F>;
+template <int F, int PA> static int ana_halo(int K, int (&H)[MAXK + 1]) {
+    using G = FGeom<F, PA>;
     H[K] = 0;
     for (int l = K; l >= 1; --l) {
         const int a = 2 * H[l] + F - 2, b = F - 2 + G::WO;
@@ -502,7 +520,7 @@ static Fused1dCfg plan_split(int64_t n, int L) {
         if (K > kcap) K = kcap;
         if (K > MAXK) K = MAXK;
         int H[MAXK + 1];
-        while (K >= 1 && (ana_halo<F>(K, H) > tile / halo_div || (tile >> K) < 4)) --K;
+        while (K >= 1 && (ana_halo<F, AnaPairs<T>::value>(K, H) > tile / halo_div || (tile >> K) < 4)) --K;
         if (K < 1) return c;
         c.st[c.nstages++] = Stage{K, (int)tile, lv};
         cur >>= K;
@@ -516,10 +534,10 @@ static Fused1dCfg plan_split(int64_t n, int L) {
     return c;
 }
 
-template <int F> static void make_ana_plan(AnaPlan &pl, const Stage &sg, int vec) {
+template <int F, int PA> static void make_ana_plan(AnaPlan &pl, const Stage &sg, int vec) {
     pl.K = sg.K; pl.tile = sg.tile;
     int H[MAXK + 1];
-    ana_halo<F>(sg.K, H);
+    ana_halo<F, PA>(sg.K, H);
     pl.h0 = (H[0] + vec - 1) / vec * vec;
     pl.NA[0] = sg.tile + pl.h0; pl.ND[0] = sg.tile;
     for (int l = 1; l <= sg.K; ++l) { pl.ND[l] = sg.tile >> l; pl.NA[l] = pl.ND[l] + H[l]; }
@@ -620,7 +638,7 @@ static int32_t run_fused_1d(const PassOp<T> &op, T *y, const T *x, int64_t n, in
         for (int i = 0; i < cfg.nstages; ++i) {
             const Stage &sg = cfg.st[i];
             AnaPlan pl;
-            make_ana_plan<F>(pl, sg, 16 / (int)sizeof(T));
+            make_ana_plan<F, AnaPairs<T>::value>(pl, sg, 16 / (int)sizeof(T));
             const size_t smem = ana_smem<T>(pl);
             auto kern = k_ana_tiles<T, F, STRICT>;
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return fail("cudaFuncSetAttribute(k_ana_tiles) failed"); }
@@ -706,6 +724,7 @@ int32_t fused_dwt(const PassOp<T> &op, T *y, const T *x, const ArrayGeom &g, int
     if (op.lifting || g.ndim != 1 || g.C != 1 || L < 1) return -1;
     if (env_int("WB200_DISABLE_FUSED", 0)) return -1;
     const int64_t n = g.dim[0];
+    if (n > ((int64_t)1 << 30)) return -1;                       // tile-relative indices are 32-bit
     if (((uintptr_t)x | (uintptr_t)y) & 15) return -1;
     if ((n * (int64_t)sizeof(T)) % 16 != 0 && g.batch > 1) return -1;
     if (op.strict) return dispatch_F<T, true>(op, y, x, n, g.batch, L, fw, workspace, ws_bytes, st);
