@@ -502,6 +502,8 @@ def test_fused_lift2d_vs_oracle(dev, mode, dtype, wname, n, L, B):
     names = _kernel_names()
     if n % 128 == 0:
         assert {"fused_lift2d_fwd", "fused_lift2d_inv"} <= names, names
+    if n in (128, 256) and L > 1:
+        assert {"fused_lift2d_tail_fwd", "fused_lift2d_tail_inv"} <= names, names
     ref = orc.dwt_lifting_batch(x, 2, wl.step, wl.norm1, wl.norm2, L)
     check(y, ref, mode, 2 * L, 8.0)
     check(xr, orc.dwt_lifting_batch(to_np(y), 2, wl.step, wl.norm1, wl.norm2, L, fw=False), mode, 2 * L, 8.0)

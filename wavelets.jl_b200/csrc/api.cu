@@ -389,12 +389,13 @@ static size_t plan_nd_from(const Call &c, int l_lo) {
     return (size_t)(g.ndim - 1) * align_up(corner * c.esize);
 }
 template <typename T>
-static size_t plan_fused2d(const PassOp<T> &op, const Call &c, int L, bool fw, bool inplace, int &Lf) {
+static size_t plan_fused2d(const PassOp<T> &op, const Call &c, int L, bool fw, bool inplace, int &Lf, bool &tail) {
     Lf = fused2d_levels<T>(op, c.g, L, fw);
-    if (Lf == 0) return 0;
-    size_t need = align_up(fused2d_scratch_bytes<T>(c.g, Lf)) + 256;
-    if (inplace) need += align_up((size_t)c.g.total() * c.esize);
-    if (L > Lf) need += plan_nd_from(c, Lf + 1);
+    tail = (L > Lf) && fused2d_tail_ok<T>(op, c.g, c.g.dim[0] >> Lf, L - Lf);
+    if (Lf == 0 && !tail) return 0;
+    size_t need = align_up(fused2d_scratch_bytes<T>(c.g, Lf > 0 ? Lf : 1)) + 512;
+    if (inplace && Lf > 0) need += align_up((size_t)c.g.total() * c.esize);
+    if (L > Lf && !tail) need += plan_nd_from(c, Lf + 1);
     return need;
 }
 
@@ -414,42 +415,55 @@ static int32_t dispatch_dwt(PassOp<T> &op, void *y, const void *x, const Call &c
         int32_t rc = fused_dwt<T>(op, (T *)y, (const T *)x, g, L, fw, workspace, ws_bytes, st, flags);
         if (rc >= 0) return rc;
     }
-    // 2-D lifting: fused level kernels for the large levels, generic passes for the small remainder
+    // 2-D lifting: fused level kernels for the large levels, then the pyramid-tail kernel (or, for shapes it does not
+    // take, the generic passes) for the small remainder
     if (!(flags & WB200_FLAG_FORCE_GENERIC) && g.C == 1 && g.ndim == 2 && lifting) {
         int Lf = 0;
-        const size_t need = plan_fused2d<T>(op, c, L, fw, inplace, Lf);
-        if (Lf > 0) {
+        bool tail = false;
+        const size_t need = plan_fused2d<T>(op, c, L, fw, inplace, Lf, tail);
+        if (Lf > 0 || tail) {
             Workspace ws;
             int32_t rc = ws.init(workspace, ws_bytes, need, st);
             if (rc != WB200_OK) return rc;
-            void *scratch = ws.take(fused2d_scratch_bytes<T>(g, Lf) + 256);
+            const int64_t N = g.dim[0], nr = N >> Lf;          // nr: corner left to the remainder
+            T *scratch = (T *)ws.take(fused2d_scratch_bytes<T>(g, Lf > 0 ? Lf : 1) + 256);
             const T *xin = (const T *)x;
-            if (inplace) { // the level kernels read x while other CTAs write y: stage a copy
+            if (inplace && Lf > 0) { // the level kernels read x while other CTAs write y: stage a copy
                 T *x0 = (T *)ws.take(bytes);
                 if (!x0 || !scratch) { set_error("internal: fused 2-D workspace plan mismatch"); return WB200_EWORKSPACE; }
                 if (!cuda_ok(cudaMemcpyAsync(x0, x, bytes, cudaMemcpyDeviceToDevice, st), "cudaMemcpyAsync")) return WB200_ECUDA;
                 xin = x0;
             }
-            const int64_t N = g.dim[0];
+            // compact buffer that carries the level-Lf approximation between the tile levels and the remainder
+            T *mid = (Lf > 0) ? (T *)((char *)scratch + (((Lf - 1) & 1) ? align_up((size_t)(N / 2) * (N / 2) * g.batch * sizeof(T)) : 0)) : nullptr;
             if (fw) {
-                rc = fused2d_run<T>(op, (T *)y, xin, nullptr, 0, 0, g, Lf, true, scratch, st);
-                if (rc != WB200_OK) return rc;
-                if (L > Lf) return run_nd<T>(op, (T *)y, (const T *)y, g, L, true, ws, Lf + 1, L);
-                return WB200_OK;
+                if (Lf > 0) {
+                    rc = fused2d_run<T>(op, (T *)y, xin, nullptr, 0, 0, g, Lf, true, scratch, st, tail && L > Lf);
+                    if (rc != WB200_OK) return rc;
+                }
+                if (L == Lf) return WB200_OK;
+                if (tail) return fused2d_tail<T>(op, Lf > 0 ? mid : xin, Lf > 0 ? nr : N, Lf > 0 ? nr * nr : N * N,
+                                                 (T *)y, N, N * N, (int)nr, L - Lf, g.batch, true, st);
+                return run_nd<T>(op, (T *)y, (const T *)y, g, L, true, ws, Lf + 1, L);
             }
-            if (L <= Lf) return fused2d_run<T>(op, (T *)y, xin, xin, N, N * N, g, Lf, false, scratch, st);
+            if (L == Lf) return fused2d_run<T>(op, (T *)y, xin, xin, N, N * N, g, Lf, false, scratch, st);
+            if (tail) {
+                if (Lf == 0) return fused2d_tail<T>(op, xin, N, N * N, (T *)y, N, N * N, (int)N, L, g.batch, false, st);
+                rc = fused2d_tail<T>(op, xin, N, N * N, mid, nr, nr * nr, (int)nr, L - Lf, g.batch, false, st);
+                if (rc != WB200_OK) return rc;
+                return fused2d_run<T>(op, (T *)y, xin, mid, nr, nr * nr, g, Lf, false, scratch, st);
+            }
             rc = run_nd<T>(op, (T *)y, xin, g, L, false, ws, Lf + 1, L);
             if (rc != WB200_OK) return rc;
             if (Lf >= 2) // level Lf reads y's corner and writes scratch; y itself is only written by level 1, later
                 return fused2d_run<T>(op, (T *)y, xin, (const T *)y, N, N * N, g, Lf, false, scratch, st);
             // Lf == 1: the single fused level would read y's corner while other CTAs overwrite y -> park the corner
-            const int64_t nf = N >> 1;
             View<const T> vs; View<T> vd; Extent e;
-            e.len = nf; e.n[0] = 1; e.n[1] = nf; e.n[2] = 1; e.n[3] = g.batch;
+            e.len = nr; e.n[0] = 1; e.n[1] = nr; e.n[2] = 1; e.n[3] = g.batch;
             vs.p = (const T *)y; vs.ls = 1; vs.s[0] = 0; vs.s[1] = N; vs.s[2] = 0; vs.s[3] = N * N;
-            vd.p = (T *)scratch; vd.ls = 1; vd.s[0] = 0; vd.s[1] = nf; vd.s[2] = 0; vd.s[3] = nf * nf;
+            vd.p = scratch; vd.ls = 1; vd.s[0] = 0; vd.s[1] = nr; vd.s[2] = 0; vd.s[3] = nr * nr;
             if (!launch_copy_lines<T>(vs, vd, e, st)) return WB200_ECUDA;
-            return fused2d_run<T>(op, (T *)y, xin, (const T *)scratch, nf, nf * nf, g, Lf, false, scratch, st);
+            return fused2d_run<T>(op, (T *)y, xin, (const T *)scratch, nr, nr * nr, g, Lf, false, scratch, st);
         }
     }
     Workspace ws;

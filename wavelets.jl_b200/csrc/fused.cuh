@@ -25,6 +25,15 @@ template <typename T> size_t fused2d_scratch_bytes(const ArrayGeom &g, int Lf);
 // from x; the result fills y.   x must not alias y; ll_src must not alias y when Lf == 1.
 template <typename T>
 int32_t fused2d_run(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int64_t ll_ld, int64_t ll_bs,
-                    const ArrayGeom &g, int Lf, bool fw, void *scratch, cudaStream_t st);
+                    const ArrayGeom &g, int Lf, bool fw, void *scratch, cudaStream_t st, bool ll_to_scratch = false);
+// (forward, ll_to_scratch: the level-Lf approximation stays in the scratch ping-pong buffer (Lf-1)&1, compact,
+//  for the pyramid-tail kernel instead of going to y's corner)
+
+// Pyramid tail: all `levels` remaining levels of an nt x nt (nt <= 128) approximation per image in one launch.
+// forward: src (plain nt x nt) -> dst = the corner's Mallat pyramid; inverse: src = pyramid -> dst plain nt x nt.
+template <typename T> bool fused2d_tail_ok(const PassOp<T> &op, const ArrayGeom &g, int64_t nt, int levels);
+template <typename T>
+int32_t fused2d_tail(const PassOp<T> &op, const T *src, int64_t ld_s, int64_t bs_s, T *dst, int64_t ld_d, int64_t bs_d,
+                     int nt, int levels, int64_t B, bool fw, cudaStream_t st);
 
 } // namespace wb

@@ -404,6 +404,127 @@ k_lift2d_inv(const T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll, const T *__
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// pyramid tail: every remaining level of an n x n (n <= 128) approximation in ONE launch, one CTA per image.
+// In-place lifting on the dyadic lattice in shared memory (level l works on the samples whose indices are
+// multiples of 2^(l-1)); any lifting scheme (runtime step table).  The coefficients are scattered to / gathered
+// from their Mallat-pyramid positions by index arithmetic at the store / load.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pyr_pos(int i, int j, int n, int levels, int &oi, int &oj) {
+    const int tzi = __ffs(i | n) - 1, tzj = __ffs(j | n) - 1;   // trailing zeros, capped by those of n (>= levels)
+    const int tz = tzi < tzj ? tzi : tzj;
+    if (tz >= levels) { oi = i >> levels; oj = j >> levels; return; }
+    const int ii = i >> tz, jj = j >> tz;                        // lattice coordinates at level tz+1 (one of them odd)
+    const int hh = (n >> tz) >> 1;
+    oi = (ii & 1) * hh + (ii >> 1);
+    oj = (jj & 1) * hh + (jj >> 1);
+}
+
+// one 1-level lifting pass over the lattice lines: line l = base + l*ls, sample k of a line at + k*ps
+template <typename T, bool STRICT, bool FW>
+__device__ __forceinline__ void tail_pass(T *A, int nl, int ls, int ps, bool line_fast, const LiftScheme<T> &sc) {
+    using fp = FP<STRICT>;
+    const int half = nl >> 1;
+    const int total = nl * half;
+    if (!FW) { // normalize! precedes the steps on the inverse path
+        for (int idx = threadIdx.x; idx < nl * nl; idx += blockDim.x) {
+            int line, k;
+            if (line_fast) { line = idx % nl; k = idx / nl; } else { k = idx % nl; line = idx / nl; }
+            T *e = A + line * ls + k * ps;
+            *e = fp::mul(*e, (k & 1) ? sc.norm2 : sc.norm1);
+        }
+        __syncthreads();
+    }
+    for (int st = 0; st < sc.nsteps; ++st) {
+        const int sh = sc.shift[st], nc = sc.nc[st];
+        const bool pred = sc.is_predict[st] != 0;
+        const int left = sh > 0 ? sh : 0;
+        for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            int line, p;
+            if (line_fast) { line = idx % nl; p = idx / nl; } else { p = idx % half; line = idx / half; }
+            T *L0 = A + line * ls;
+            T *tg = L0 + (2 * p + (pred ? 0 : 1)) * ps;
+            const int opar = pred ? 1 : 0;
+            T v = *tg;
+            const bool interior = (p >= left) && (p <= half + sh - nc) && (nc <= 3);
+            if (interior && nc > 1) {
+                T acc = fp::mul(sc.coef[st][0], L0[(2 * (p - sh) + opar) * ps]);
+                for (int k = 1; k < nc; ++k) acc = fp::mac(acc, sc.coef[st][k], L0[(2 * (p + k - sh) + opar) * ps]);
+                v = fp::add(v, acc);
+            } else {
+                for (int k = 0; k < nc; ++k) {
+                    int q = (p + k - sh) % half;
+                    if (q < 0) q += half;
+                    v = fp::mac(v, sc.coef[st][k], L0[(2 * q + opar) * ps]);
+                }
+            }
+            *tg = v;
+        }
+        __syncthreads();
+    }
+    if (FW) {
+        for (int idx = threadIdx.x; idx < nl * nl; idx += blockDim.x) {
+            int line, k;
+            if (line_fast) { line = idx % nl; k = idx / nl; } else { k = idx % nl; line = idx / nl; }
+            T *e = A + line * ls + k * ps;
+            *e = fp::mul(*e, (k & 1) ? sc.norm2 : sc.norm1);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(512)
+k_lift2d_tail_fwd(const T *__restrict__ src, int64_t ld_s, int64_t bs_s, T *__restrict__ y, int64_t ld_y, int64_t bs_y,
+                  int n, int levels, const __grid_constant__ LiftScheme<T> sc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *A = reinterpret_cast<T *>(smem_raw);
+    const T *sb = src + (int64_t)blockIdx.x * bs_s;
+    T *yb = y + (int64_t)blockIdx.x * bs_y;
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int i = idx % n, j = idx / n;
+        A[j * n + i] = sb[(int64_t)j * ld_s + i];
+    }
+    __syncthreads();
+    for (int l = 1; l <= levels; ++l) {
+        const int st = 1 << (l - 1), nl = n >> (l - 1);
+        tail_pass<T, STRICT, true>(A, nl, st, st * n, true, sc);       // dim-2 lines (one per lattice row index i)
+        tail_pass<T, STRICT, true>(A, nl, st * n, st, false, sc);      // dim-1 lines (one per lattice column j)
+    }
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int i = idx % n, j = idx / n;
+        int oi, oj;
+        pyr_pos(i, j, n, levels, oi, oj);
+        yb[(int64_t)oj * ld_y + oi] = A[j * n + i];
+    }
+}
+
+template <typename T, bool STRICT>
+__global__ void __launch_bounds__(512)
+k_lift2d_tail_inv(const T *__restrict__ x, int64_t ld_x, int64_t bs_x, T *__restrict__ dst, int64_t ld_d, int64_t bs_d,
+                  int n, int levels, const __grid_constant__ LiftScheme<T> sc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *A = reinterpret_cast<T *>(smem_raw);
+    const T *xb = x + (int64_t)blockIdx.x * bs_x;
+    T *db = dst + (int64_t)blockIdx.x * bs_d;
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int i = idx % n, j = idx / n;
+        int oi, oj;
+        pyr_pos(i, j, n, levels, oi, oj);
+        A[j * n + i] = xb[(int64_t)oj * ld_x + oi];
+    }
+    __syncthreads();
+    for (int l = levels; l >= 1; --l) {
+        const int st = 1 << (l - 1), nl = n >> (l - 1);
+        tail_pass<T, STRICT, false>(A, nl, st * n, st, false, sc);     // inverse order: dim 1 first
+        tail_pass<T, STRICT, false>(A, nl, st, st * n, true, sc);
+    }
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int i = idx % n, j = idx / n;
+        db[(int64_t)j * ld_d + i] = A[j * n + i];
+    }
+}
+
 // ===================================================================================================
 // host side
 // ===================================================================================================
@@ -419,6 +540,7 @@ template <typename T> static void fill_coefs(LiftCoefs<T> &lc, const LiftScheme<
 }
 
 template <typename T> struct Tile2d { static constexpr int TI = 128, TJ = 64; };
+constexpr int TAIL2D_MAX = 64;    // largest corner handed to the pyramid-tail kernel (latency-bound: one CTA per image)
 
 template <class S, typename T> using CfgFor = Cfg2d<S, Tile2d<T>::TI, Tile2d<T>::TJ, 16, 16>;
 
@@ -446,8 +568,34 @@ int fused2d_levels(const PassOp<T> &op, const ArrayGeom &g, int L, bool fw) {
     int Lf = 0;
     int64_t n = g.dim[0];
     if (n > (int64_t)1 << 30) return 0;
-    while (Lf < L && n >= tmax && n % Tile2d<T>::TI == 0 && n % Tile2d<T>::TJ == 0) { ++Lf; n >>= 1; }
+    // corners of 128 and below belong to the pyramid-tail kernel (one launch for all of them)
+    while (Lf < L && n >= tmax && n > TAIL2D_MAX && n % Tile2d<T>::TI == 0 && n % Tile2d<T>::TJ == 0) { ++Lf; n >>= 1; }
     return Lf;
+}
+
+template <typename T>
+bool fused2d_tail_ok(const PassOp<T> &op, const ArrayGeom &g, int64_t nt, int levels) {
+    if (!op.lifting || g.ndim != 2 || g.C != 1 || g.dim[0] != g.dim[1]) return false;
+    if (env_int2("WB200_DISABLE_FUSED2D", 0) || env_int2("WB200_DISABLE_TAIL2D", 0)) return false;
+    return levels >= 1 && nt >= 2 && nt <= TAIL2D_MAX && g.batch <= 0x7fffffff;
+}
+
+template <typename T>
+int32_t fused2d_tail(const PassOp<T> &op, const T *src, int64_t ld_s, int64_t bs_s, T *dst, int64_t ld_d, int64_t bs_d,
+                     int nt, int levels, int64_t B, bool fw, cudaStream_t st) {
+    const size_t smem = (size_t)nt * nt * sizeof(T);
+#define WB_TAIL(KERN, NAME)                                                                                        \
+    {                                                                                                              \
+        auto kern = KERN;                                                                                          \
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {   \
+            (void)cudaGetLastError(); set_error("cudaFuncSetAttribute(" NAME ") failed"); return WB200_ECUDA; }     \
+        LaunchScope scope(NAME, st);                                                                               \
+        kern<<<(unsigned)B, 512, smem, st>>>(src, ld_s, bs_s, dst, ld_d, bs_d, nt, levels, op.sc);                  \
+    }
+    if (fw) { if (op.strict) WB_TAIL((k_lift2d_tail_fwd<T, true>), "fused_lift2d_tail_fwd") else WB_TAIL((k_lift2d_tail_fwd<T, false>), "fused_lift2d_tail_fwd") }
+    else    { if (op.strict) WB_TAIL((k_lift2d_tail_inv<T, true>), "fused_lift2d_tail_inv") else WB_TAIL((k_lift2d_tail_inv<T, false>), "fused_lift2d_tail_inv") }
+#undef WB_TAIL
+    return check_launch("fused_lift2d_tail") ? WB200_OK : WB200_ECUDA;
 }
 
 template <typename T> size_t fused2d_scratch_bytes(const ArrayGeom &g, int Lf) {
@@ -455,7 +603,7 @@ template <typename T> size_t fused2d_scratch_bytes(const ArrayGeom &g, int Lf) {
     if (Lf < 1) return 0;
     const size_t n = (size_t)g.dim[0];
     size_t b0 = (n / 2) * (n / 2) * (size_t)g.batch * sizeof(T);
-    size_t b1 = (Lf >= 3) ? (n / 4) * (n / 4) * (size_t)g.batch * sizeof(T) : 0;
+    size_t b1 = (Lf >= 2) ? (n / 4) * (n / 4) * (size_t)g.batch * sizeof(T) : 0;
     return ((b0 + 255) & ~(size_t)255) + ((b1 + 255) & ~(size_t)255);
 }
 
@@ -482,7 +630,7 @@ static int32_t launch_level(const T *a, int64_t lda, int64_t bsa, const T *xd, i
 
 template <typename T, class SF, class SI_, bool STRICT>
 static int32_t run2d(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int64_t ll_ld, int64_t ll_bs,
-                     const ArrayGeom &g, int Lf, bool fw, void *scratch, cudaStream_t st) {
+                     const ArrayGeom &g, int Lf, bool fw, void *scratch, cudaStream_t st, bool ll_to_scratch) {
     const int64_t N = g.dim[0], B = g.batch;
     const int64_t bsN = N * N;
     LiftCoefs<T> lc;
@@ -498,7 +646,7 @@ static int32_t run2d(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int
             const T *src = (l == 1) ? x : buf[(l - 2) & 1];
             const int64_t lds = (l == 1) ? N : n, bss = (l == 1) ? bsN : (int64_t)n * n;
             T *llo; int64_t ldl, bsl;
-            if (l == Lf) { llo = y; ldl = N; bsl = bsN; }                       // final approximation: y's corner
+            if (l == Lf && !ll_to_scratch) { llo = y; ldl = N; bsl = bsN; }     // final approximation: y's corner
             else         { llo = buf[(l - 1) & 1]; ldl = n / 2; bsl = (int64_t)(n / 2) * (n / 2); }
             int32_t rc = launch_level<T, SF, STRICT, true>(src, lds, bss, nullptr, 0, 0, llo, ldl, bsl, y, N, bsN, n, B, lc, st);
             if (rc != WB200_OK) return rc;
@@ -521,11 +669,11 @@ static int32_t run2d(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int
 
 template <typename T>
 int32_t fused2d_run(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int64_t ll_ld, int64_t ll_bs,
-                    const ArrayGeom &g, int Lf, bool fw, void *scratch, cudaStream_t st) {
+                    const ArrayGeom &g, int Lf, bool fw, void *scratch, cudaStream_t st, bool ll_to_scratch) {
     const int id = shape_id<T>(op.sc, fw);
 #define WB_RUN(SF, SI_)                                                                                            \
-    return op.strict ? run2d<T, SF, SI_, true>(op, y, x, ll_src, ll_ld, ll_bs, g, Lf, fw, scratch, st)              \
-                     : run2d<T, SF, SI_, false>(op, y, x, ll_src, ll_ld, ll_bs, g, Lf, fw, scratch, st)
+    return op.strict ? run2d<T, SF, SI_, true>(op, y, x, ll_src, ll_ld, ll_bs, g, Lf, fw, scratch, st, ll_to_scratch)   \
+                     : run2d<T, SF, SI_, false>(op, y, x, ll_src, ll_ld, ll_bs, g, Lf, fw, scratch, st, ll_to_scratch)
     switch (id) {
     case 1: WB_RUN(ShapeCdf97F, ShapeCdf97I);
     case 2: WB_RUN(ShapeHaarF, ShapeHaarI);
@@ -538,7 +686,9 @@ int32_t fused2d_run(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int6
 #define WB_INST(T)                                                                                                 \
     template int fused2d_levels<T>(const PassOp<T> &, const ArrayGeom &, int, bool);                                \
     template size_t fused2d_scratch_bytes<T>(const ArrayGeom &, int);                                               \
-    template int32_t fused2d_run<T>(const PassOp<T> &, T *, const T *, const T *, int64_t, int64_t, const ArrayGeom &, int, bool, void *, cudaStream_t);
+    template int32_t fused2d_run<T>(const PassOp<T> &, T *, const T *, const T *, int64_t, int64_t, const ArrayGeom &, int, bool, void *, cudaStream_t, bool); \
+    template bool fused2d_tail_ok<T>(const PassOp<T> &, const ArrayGeom &, int64_t, int);                          \
+    template int32_t fused2d_tail<T>(const PassOp<T> &, const T *, int64_t, int64_t, T *, int64_t, int64_t, int, int, int64_t, bool, cudaStream_t);
 WB_INST(float)
 WB_INST(double)
 #undef WB_INST
