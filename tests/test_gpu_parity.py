@@ -500,9 +500,12 @@ def test_fused_lift2d_vs_oracle(dev, mode, dtype, wname, n, L, B):
     xr = wb.idwtc(y, wl, L)
     _lib.lib().wb200_profile_enable(0)
     names = _kernel_names()
-    if n % 128 == 0:
+    lt, m = 0, n                      # levels taken by the tile kernels (corner >= 128, multiple of the tile)
+    while lt < L and m >= 128 and m % 128 == 0:
+        lt, m = lt + 1, m // 2
+    if lt:
         assert {"fused_lift2d_fwd", "fused_lift2d_inv"} <= names, names
-    if n in (128, 256) and L > 1:
+    if L > lt and m <= 64:            # the remainder goes to the one-launch pyramid tail
         assert {"fused_lift2d_tail_fwd", "fused_lift2d_tail_inv"} <= names, names
     ref = orc.dwt_lifting_batch(x, 2, wl.step, wl.norm1, wl.norm2, L)
     check(y, ref, mode, 2 * L, 8.0)

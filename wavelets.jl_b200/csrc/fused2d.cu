@@ -404,6 +404,10 @@ k_lift2d_inv(const T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll, const T *__
     }
 }
 
+} // namespace wb
+#include "fused2d_tma.cuh"
+namespace wb {
+
 // ---------------------------------------------------------------------------------------------------
 // pyramid tail: every remaining level of an n x n (n <= 128) approximation in ONE launch, one CTA per image.
 // In-place lifting on the dyadic lattice in shared memory (level l works on the samples whose indices are
@@ -607,10 +611,47 @@ template <typename T> size_t fused2d_scratch_bytes(const ArrayGeom &g, int Lf) {
     return ((b0 + 255) & ~(size_t)255) + ((b1 + 255) & ~(size_t)255);
 }
 
+template <class S, typename T> using Cfg3For = Cfg3<T, S, Tile2d<T>::TI, Tile2d<T>::TJ, 16, 16>;
+
 template <typename T, class S, bool STRICT, bool FW>
 static int32_t launch_level(const T *a, int64_t lda, int64_t bsa, const T *xd, int64_t ldx, int64_t bsx,
                             T *o1, int64_t ld1, int64_t bs1, T *o2, int64_t ld2, int64_t bs2,
                             int n, int64_t B, const LiftCoefs<T> &lc, cudaStream_t st) {
+    // ---- preferred: tensor-map TMA tiles ----
+    if (env_int2("WB200_LIFT2D_TMA", 1)) {
+        using C3 = Cfg3For<S, T>;
+        dim3 grid((unsigned)(n / C3::TI), (unsigned)(n / C3::TJ), (unsigned)B);
+        if constexpr (FW) {
+            TensorMap tm;
+            if (make_tensor_map<T>(tm, a, n, n, B, lda, bsa, C3::PI, C3::RJ)) {
+                auto kern = k_lift2d_fwd_tma<T, S, STRICT, C3>;
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3::SMEM_F) == cudaSuccess) {
+                    {
+                        LaunchScope scope("fused_lift2d_fwd", st);
+                        kern<<<grid, C3::NT, C3::SMEM_F, st>>>(tm, a, lda, bsa, o1, ld1, bs1, o2, ld2, bs2, n, lc);
+                    }
+                    return check_launch("fused_lift2d_fwd(tma)") ? WB200_OK : WB200_ECUDA;
+                }
+                (void)cudaGetLastError();
+            }
+        } else {
+            TensorMap tml, tmx;
+            const int nh = n / 2;
+            if (make_tensor_map<T>(tml, a, nh, nh, B, lda, bsa, C3::PC, C3::JQ) &&
+                make_tensor_map<T>(tmx, xd, n, n, B, ldx, bsx, C3::PC, C3::JQ)) {
+                auto kern = k_lift2d_inv_tma<T, S, STRICT, C3>;
+                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3::SMEM_I) == cudaSuccess) {
+                    {
+                        LaunchScope scope("fused_lift2d_inv", st);
+                        kern<<<grid, C3::NT, C3::SMEM_I, st>>>(tml, tmx, a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, n, lc);
+                    }
+                    return check_launch("fused_lift2d_inv(tma)") ? WB200_OK : WB200_ECUDA;
+                }
+                (void)cudaGetLastError();
+            }
+        }
+    }
+    // ---- fallback: cp.async staging ----
     using C = CfgFor<S, T>;
     const size_t smem = (size_t)2 * C::RJ * C::P * sizeof(T);
     dim3 grid((unsigned)(n / C::TI), (unsigned)(n / C::TJ), (unsigned)B);
