@@ -261,20 +261,45 @@ k_ana_tiles(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, in
     }
 }
 
-// whole-line tail: the CTA owns a column of length m (<= what fits), runs `levels` analysis levels in shared memory.
-// Scalar closed-form evaluation with periodic indexing (valid for any m_l >= 2, including m_l < F).
+// whole-line tail: the CTA owns a column of length m (<= what fits) and runs `levels` analysis levels in shared
+// memory.  Levels of 64 samples and more reuse the vectorised tile routine on a line with its periodic wrap copied
+// behind it; shorter levels (any m_l >= 2, including m_l < F) use a scalar closed form with modular indexing.
+template <typename T, int F> struct TailGeom {
+    static constexpr int PA = AnaPairs<T>::value;
+    using G = FGeom<F, PA>;
+    static constexpr int HW = (F + G::WO + 2 + 3) & ~3;      // wrap samples appended to a line (multiple of 4)
+};
+
 template <typename T, int F, bool STRICT>
 __global__ void __launch_bounds__(256)
 k_ana_tail(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, int64_t n, int m, int levels, int first_level,
            const __grid_constant__ Taps<T, F> c) {
     using fp = FP<STRICT>;
+    using TG = TailGeom<T, F>;
+    constexpr int PA = TG::PA;
+    using G = typename TG::G;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *bufA = reinterpret_cast<T *>(smem_raw);
-    T *bufB = bufA + ((m + 3) & ~3);
+    T *bufB = bufA + ((m + TG::HW + 3) & ~3);
     const int64_t col = blockIdx.x;
     const T *sc = src + col * src_stride;
     T *yc = y + col * n;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) bufA[i] = sc[i];
+    // the column arrives with one TMA bulk copy when it is 16-byte granular, else with plain loads
+    __shared__ __align__(8) uint64_t tbar;
+    const bool bulk = ((m * (int)sizeof(T)) % 16 == 0) && ((reinterpret_cast<uintptr_t>(sc) & 15) == 0);
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(&tbar, 1);
+            mbar_expect_tx(&tbar, (uint32_t)(m * sizeof(T)));
+            tma_bulk_g2s(bufA, sc, (uint32_t)(m * sizeof(T)), &tbar);
+        }
+        __syncthreads();
+        mbar_wait(&tbar, 0);
+    } else {
+        for (int i = threadIdx.x; i < m; i += blockDim.x) bufA[i] = sc[i];
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < TG::HW; i += blockDim.x) bufA[m + i] = bufA[i % m];
     __syncthreads();
     T *in = bufA, *out = bufB;
     int ml = m;
@@ -283,24 +308,45 @@ k_ana_tail(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, int
         const int lvl = first_level + l;             // absolute level number
         T *dband = yc + (n >> lvl);
         const bool last = (l == levels);
-        for (int k = threadIdx.x; k < nh; k += blockDim.x) {
-            int ia = 2 * k;                          // < ml
-            T a = fp::mul(c.h[0], in[ia]);
-#pragma unroll
-            for (int q = 1; q < F; ++q) {
-                if (++ia == ml) ia = 0;
-                a = fp::mac(a, c.h[q], in[ia]);
+        if (ml >= 64 && (nh % PA) == 0) {
+            auto store_d = [&](int p, const T (&d)[PA]) {
+                int idx = p + G::DS;
+                if (idx >= nh) idx -= nh;
+                if constexpr (PA == 2) gstore2(dband + idx, d[0], d[1]); else __stcs(dband + idx, d[0]);
+            };
+            if (last) {
+                auto store_a = [&](int p, const T (&a)[PA]) {
+                    if constexpr (PA == 2) gstore2(yc + p, a[0], a[1]); else __stcs(yc + p, a[0]);
+                };
+                ana_level<T, F, STRICT>(in, nh, nh, c, store_a, store_d);
+            } else {
+                auto store_a = [&](int p, const T (&a)[PA]) {
+                    if constexpr (PA == 2) store2(out + p, a[0], a[1]); else out[p] = a[0];
+                };
+                ana_level<T, F, STRICT>(in, nh, nh, c, store_a, store_d);
+                __syncthreads();
+                for (int i = threadIdx.x; i < TG::HW; i += blockDim.x) out[nh + i] = out[i % nh];   // periodic wrap
             }
-            int id = (2 * k + 2 - F) % ml;
-            if (id < 0) id += ml;
-            T d = fp::mul(c.g[F - 1], in[id]);
+        } else {
+            for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+                int ia = 2 * k;                          // < ml
+                T a = fp::mul(c.h[0], in[ia]);
 #pragma unroll
-            for (int q = 1; q < F; ++q) {
-                if (++id == ml) id = 0;
-                d = fp::mac(d, c.g[F - 1 - q], in[id]);
+                for (int q = 1; q < F; ++q) {
+                    if (++ia == ml) ia = 0;
+                    a = fp::mac(a, c.h[q], in[ia]);
+                }
+                int id = (2 * k + 2 - F) % ml;
+                if (id < 0) id += ml;
+                T d = fp::mul(c.g[F - 1], in[id]);
+#pragma unroll
+                for (int q = 1; q < F; ++q) {
+                    if (++id == ml) id = 0;
+                    d = fp::mac(d, c.g[F - 1 - q], in[id]);
+                }
+                dband[k] = d;
+                if (last) yc[k] = a; else out[k] = a;
             }
-            dband[k] = d;
-            if (last) yc[k] = a; else out[k] = a;
         }
         __syncthreads();
         T *t = in; in = out; out = t;
@@ -378,21 +424,24 @@ k_syn_tiles(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restrict
     const T *xc = x + col * n0;
     const int K = pl.K;
 
+    // one mbarrier per level (bar[l] covers d_l; bar[K] also the approximation): the coarse levels start while the
+    // large fine-level detail slices are still in flight
     if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        uint32_t bytes = 0;
-        for (int l = 1; l <= K; ++l) bytes += (uint32_t)((pl.dhi[l] - pl.dlo[l]) * sizeof(T));
-        bytes += (uint32_t)((pl.rhi[K] - pl.rlo[K]) * sizeof(T));
-        mbar_expect_tx(bar, bytes);
-        tma_load_wrapped<T>(sm + pl.aoff, asrc + col * asrc_stride, (s >> K) + pl.rlo[K], pl.rhi[K] - pl.rlo[K], ncur >> K, bar);
-        for (int l = K; l >= 1; --l)
-            tma_load_wrapped<T>(sm + pl.doff[l], xc + (n0 >> (lvl0 + l)), (s >> l) + pl.dlo[l], pl.dhi[l] - pl.dlo[l], ncur >> l, bar);
+        for (int l = 1; l <= K; ++l) mbar_init(bar + l, 1);
+        for (int l = K; l >= 1; --l) {
+            uint32_t bytes = (uint32_t)((pl.dhi[l] - pl.dlo[l]) * sizeof(T));
+            if (l == K) bytes += (uint32_t)((pl.rhi[K] - pl.rlo[K]) * sizeof(T));
+            mbar_expect_tx(bar + l, bytes);
+            if (l == K)
+                tma_load_wrapped<T>(sm + pl.aoff, asrc + col * asrc_stride, (s >> K) + pl.rlo[K], pl.rhi[K] - pl.rlo[K], ncur >> K, bar + l);
+            tma_load_wrapped<T>(sm + pl.doff[l], xc + (n0 >> (lvl0 + l)), (s >> l) + pl.dlo[l], pl.dhi[l] - pl.dlo[l], ncur >> l, bar + l);
+        }
     }
     __syncthreads();
-    mbar_wait(bar, 0);
 
     const T *abuf = sm + pl.aoff;
     for (int l = K; l >= 1; --l) {
+        mbar_wait(bar + l, 0);
         // produce the approximation one level up on [s_{l-1} + rlo[l-1], s_{l-1} + rhi[l-1])
         const int npairs = (pl.rhi[l - 1] - pl.rlo[l - 1]) >> 1;           // output pairs = values of u
         const int oa = (pl.rlo[l - 1] >> 1) - pl.rlo[l];                   // index of a[u_first] inside abuf
@@ -412,51 +461,118 @@ k_syn_tiles(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restrict
     }
 }
 
-// whole-line inverse tail: x[0:m) = [a_L | d_L | ... | d_{lv0+1}] of a column -> a_{lv0} (m samples)
+// whole-line inverse tail: x[0:m) = [a_L | d_L | ... | d_{lv0+1}] of a column -> a_{lv0} (m samples).
+// The bands are staged with gaps: every detail band is followed by its periodic wrap (QD samples) and every
+// approximation buffer is preceded by its wrap (QAP samples), so that levels of 32+ samples run the vectorised
+// tile routine; shorter levels use the scalar closed form.
+template <typename T, int F> struct SynTailGeom {
+    using G = FGeom<F>;
+    static constexpr int QAP = (G::QA + 3) & ~3;          // left wrap slots in front of an approximation (multiple of 4)
+    static constexpr int QDP = (G::QD + 3) & ~3;          // right wrap slots behind a detail band
+    // element offset of detail band t (t = 0: d_L with mL samples, t: mL * 2^t samples) in the staged layout
+    __host__ __device__ static int band_off(int mL, int t) {
+        int off = QAP + ((mL + 3) & ~3);
+        for (int u = 0; u < t; ++u) off += (((mL << u) + QDP + 3) & ~3);
+        return off;
+    }
+};
+
 template <typename T, int F, bool STRICT>
 __global__ void __launch_bounds__(256)
 k_syn_tail(const T *__restrict__ x, int64_t n, T *__restrict__ dst, int64_t dst_stride, int m, int levels,
            const __grid_constant__ Taps<T, F> c) {
     using fp = FP<STRICT>;
+    using SG = SynTailGeom<T, F>;
+    using G = FGeom<F>;
     constexpr int Q = F / 2;
+    constexpr int QAP = SG::QAP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *xin = reinterpret_cast<T *>(smem_raw);       // the m input coefficients
-    T *bufP = xin + ((m + 3) & ~3);                 // outputs of levels levels-2, levels-4, ... (<= m/2 samples)
-    T *bufQ = bufP + (((m >> 1) + 3) & ~3);         // outputs of levels levels-3, levels-5, ... (<= m/4 samples)
+    T *stage = reinterpret_cast<T *>(smem_raw);             // [QAP | a_L][d_L | wrap][d_{L-1} | wrap] ...
+    const int mL = m >> levels;
+    const int stage_sz = SG::band_off(mL, levels);
+    T *bufP = stage + ((stage_sz + 3) & ~3);                // approximations produced at levels-2, levels-4, ... (<= m/2)
+    T *bufQ = bufP + ((QAP + (m >> 1) + 3) & ~3);           // ... at levels-3, levels-5, ...                 (<= m/4)
     const int64_t col = blockIdx.x;
     const T *xc = x + col * n;
     T *dc = dst + col * dst_stride;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) xin[i] = xc[i];
+    // ---- stage the coefficients: one TMA bulk copy per band that is 16-byte granular, plain loads for the small ones;
+    //      then the periodic wraps from shared memory ----
+    __shared__ __align__(8) uint64_t tbar;
+    constexpr int V = 16 / (int)sizeof(T);
+    const bool aligned = (reinterpret_cast<uintptr_t>(xc) & 15) == 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&tbar, 1);
+        uint32_t bytes = 0;
+        if (aligned && mL % V == 0) bytes += (uint32_t)(mL * sizeof(T));
+        for (int t = 0; t < levels; ++t) if (aligned && (mL << t) % V == 0) bytes += (uint32_t)((mL << t) * sizeof(T));
+        mbar_expect_tx(&tbar, bytes);
+        if (aligned && mL % V == 0) tma_bulk_g2s(stage + QAP, xc, (uint32_t)(mL * sizeof(T)), &tbar);
+        for (int t = 0; t < levels; ++t)
+            if (aligned && (mL << t) % V == 0)
+                tma_bulk_g2s(stage + SG::band_off(mL, t), xc + (mL << t), (uint32_t)((mL << t) * sizeof(T)), &tbar);
+    }
+    if (!(aligned && mL % V == 0))
+        for (int i = threadIdx.x; i < mL; i += blockDim.x) stage[QAP + i] = xc[i];
+    for (int t = 0; t < levels; ++t) {
+        const int sz = mL << t;
+        if (!(aligned && sz % V == 0))
+            for (int i = threadIdx.x; i < sz; i += blockDim.x) stage[SG::band_off(mL, t) + i] = xc[sz + i];
+    }
     __syncthreads();
-    int nh = m >> levels;                           // current approximation length
-    const T *a = xin;
+    mbar_wait(&tbar, 0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < QAP; i += blockDim.x) { int k = (mL - 1 - i) % mL; if (k < 0) k += mL; stage[QAP - 1 - i] = stage[QAP + k]; }
+    for (int t = 0; t < levels; ++t) {
+        const int sz = mL << t, off = SG::band_off(mL, t);
+        for (int i = threadIdx.x; i < SG::QDP; i += blockDim.x) stage[off + sz + i] = stage[off + (i % sz)];
+    }
+    __syncthreads();
+    int nh = mL;                                            // current approximation length
+    T *a = stage;                                           // a[QAP + i] = approximation sample i
     for (int l = 0; l < levels; ++l) {
-        const T *d = xin + nh;                      // details of this level follow the coarser coefficients
+        const T *d = stage + SG::band_off(mL, l);           // d[i], i in [0, nh + QDP)
         const bool last = (l == levels - 1);
-        T *out = ((levels - 2 - l) & 1) ? bufQ : bufP;
-        for (int u = threadIdx.x; u < nh; u += blockDim.x) {
-            int ia = (u - (Q - 1)) % nh;
-            if (ia < 0) ia += nh;
-            T rae = fp::mul(c.h[2 * (Q - 1)], a[ia]);
-            T rao = fp::mul(c.h[2 * (Q - 1) + 1], a[ia]);
-#pragma unroll
-            for (int k = Q - 2; k >= 0; --k) {
-                if (++ia == nh) ia = 0;
-                rae = fp::mac(rae, c.h[2 * k], a[ia]);
-                rao = fp::mac(rao, c.h[2 * k + 1], a[ia]);
+        T *out = ((levels - 2 - l) & 1) ? bufQ : bufP;      // out[QAP + i]
+        if (nh >= 32 && (nh & 1) == 0) {
+            if (last) {
+                auto so = [&](int ur, T o0, T o1, T o2, T o3) { gstore4(dc + 2 * ur, o0, o1, o2, o3); };
+                syn_level<T, F, STRICT>(a, d, QAP, 0, nh, c, so);
+            } else {
+                auto so = [&](int ur, T o0, T o1, T o2, T o3) { store4(out + QAP + 2 * ur, o0, o1, o2, o3); };
+                syn_level<T, F, STRICT>(a, d, QAP, 0, nh, c, so);
+                __syncthreads();
+                for (int i = threadIdx.x; i < QAP; i += blockDim.x) out[QAP - 1 - i] = out[QAP + 2 * nh - 1 - i];   // left wrap
             }
-            int id = u;
-            T rde = fp::mul(c.g[1], d[id]);
-            T rdo = fp::mul(c.g[0], d[id]);
+        } else {
+            for (int u = threadIdx.x; u < nh; u += blockDim.x) {
+                int ia = (u - (Q - 1)) % nh;
+                if (ia < 0) ia += nh;
+                T rae = fp::mul(c.h[2 * (Q - 1)], a[QAP + ia]);
+                T rao = fp::mul(c.h[2 * (Q - 1) + 1], a[QAP + ia]);
 #pragma unroll
-            for (int k = 1; k < Q; ++k) {
-                if (++id == nh) id = 0;
-                rde = fp::mac(rde, c.g[2 * k + 1], d[id]);
-                rdo = fp::mac(rdo, c.g[2 * k], d[id]);
+                for (int k = Q - 2; k >= 0; --k) {
+                    if (++ia == nh) ia = 0;
+                    rae = fp::mac(rae, c.h[2 * k], a[QAP + ia]);
+                    rao = fp::mac(rao, c.h[2 * k + 1], a[QAP + ia]);
+                }
+                int id = u;
+                T rde = fp::mul(c.g[1], d[id]);
+                T rdo = fp::mul(c.g[0], d[id]);
+#pragma unroll
+                for (int k = 1; k < Q; ++k) {
+                    if (++id == nh) id = 0;
+                    rde = fp::mac(rde, c.g[2 * k + 1], d[id]);
+                    rdo = fp::mac(rdo, c.g[2 * k], d[id]);
+                }
+                const T x0 = fp::add(rae, rde), x1 = fp::add(rao, rdo);
+                if (last) { dc[2 * u] = x0; dc[2 * u + 1] = x1; }
+                else      { out[QAP + 2 * u] = x0; out[QAP + 2 * u + 1] = x1; }
             }
-            const T x0 = fp::add(rae, rde), x1 = fp::add(rao, rdo);
-            if (last) { dc[2 * u] = x0; dc[2 * u + 1] = x1; }
-            else      { out[2 * u] = x0; out[2 * u + 1] = x1; }
+            if (!last) {
+                __syncthreads();
+                const int no = 2 * nh;
+                for (int i = threadIdx.x; i < QAP; i += blockDim.x) { int k = (no - 1 - i) % no; if (k < 0) k += no; out[QAP - 1 - i] = out[QAP + k]; }
+            }
         }
         __syncthreads();
         a = out;
@@ -486,7 +602,9 @@ struct Fused1dCfg {
     int64_t m = 0;         // tail line length (n >> tail_lv0)
 };
 
-template <typename T> static int tail_max() { return sizeof(T) == 4 ? env_int("WB200_TAILMAX_F32", 16384) : env_int("WB200_TAILMAX_F64", 8192); }
+// defaults from the r01 sweep (tools/tune_fused1d.py, profiles/r01_tune_*.log): fewer fused levels (smaller halo) and a
+// larger whole-line tail win once the tails load with TMA
+template <typename T> static int tail_max() { return sizeof(T) == 4 ? env_int("WB200_TAILMAX_F32", 32768) : env_int("WB200_TAILMAX_F64", 16384); }
 template <typename T> static int tile_max() { return sizeof(T) == 4 ? env_int("WB200_TILE_F32", 8192) : env_int("WB200_TILE_F64", 4096); }
 
 template <int F, int PA> static int ana_halo(int K, int (&H)[MAXK + 1]) {
@@ -657,8 +775,10 @@ static int32_t run_fused_1d(const PassOp<T> &op, T *y, const T *x, int64_t n, in
         }
         if (cfg.tail_levels > 0) {
             const int m = (int)cfg.m;
-            const size_t smem = ((size_t)((m + 3) & ~3) + (size_t)(((m >> 1) + 3) & ~3) + 8) * sizeof(T);
+            constexpr int HW = TailGeom<T, F>::HW;
+            const size_t smem = ((size_t)((m + HW + 3) & ~3) + (size_t)(((m >> 1) + HW + 3) & ~3) + 8) * sizeof(T);
             auto kern = k_ana_tail<T, F, STRICT>;
+            if (smem > 232448) return fail("analysis tail does not fit shared memory (lower WB200_TAILMAX_*)");
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return fail("cudaFuncSetAttribute(k_ana_tail) failed"); }
             const T *src = cfg.nstages ? abuf(cfg.nstages - 1) : x;
             const int64_t sstride = cfg.nstages ? cfg.m : n;
@@ -671,8 +791,11 @@ static int32_t run_fused_1d(const PassOp<T> &op, T *y, const T *x, int64_t n, in
     } else {
         if (cfg.tail_levels > 0) {
             const int m = (int)cfg.m;
-            const size_t smem = ((size_t)((m + 3) & ~3) + (size_t)(((m >> 1) + 3) & ~3) + (size_t)(((m >> 2) + 3) & ~3) + 8) * sizeof(T);
+            using SG = SynTailGeom<T, F>;
+            const size_t smem = ((size_t)((SG::band_off(m >> cfg.tail_levels, cfg.tail_levels) + 3) & ~3) +
+                                 (size_t)((SG::QAP + (m >> 1) + 3) & ~3) + (size_t)((SG::QAP + (m >> 2) + 3) & ~3) + 16) * sizeof(T);
             auto kern = k_syn_tail<T, F, STRICT>;
+            if (smem > 232448) return fail("synthesis tail does not fit shared memory (lower WB200_TAILMAX_*)");
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return fail("cudaFuncSetAttribute(k_syn_tail) failed"); }
             T *dst = cfg.nstages ? abuf(cfg.nstages - 1) : y;
             const int64_t dstride = cfg.nstages ? cfg.m : n;
