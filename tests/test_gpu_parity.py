@@ -516,3 +516,55 @@ def test_fused_lift2d_vs_oracle(dev, mode, dtype, wname, n, L, B):
     check(z, np.asfortranarray(ref[:, :, 0]), mode, 2 * L, 8.0)
     wb.idwt_(z, wl, L)
     assert float(np.max(np.abs(to_np(z) - x[:, :, 0]))) < (1e-10 if dtype == np.float64 else 1e-4)
+
+
+# ------------------------------------------------------------------------------------------------------
+# fast single-level passes (TMA line kernels for contiguous lines, register "walk" kernels for strided lines)
+# that serve the N-D filter-bank and wavelet-packet drivers
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("wname", ["haar", "db2", "db4", "db6", "sym8", "db10"])
+def test_fastpass_nd_filter_vs_oracle(dev, mode, dtype, wname):
+    from wavelets_b200 import _lib
+    wt = wavelet(wavelet_class(wname))
+    for shape, L in (((256, 128), 3), ((512, 512), 2), ((64, 64, 64), 2), ((128, 32, 64), 1)):
+        x = rng(sum(shape) + L).standard_normal(shape).astype(dtype)
+        _lib.lib().wb200_profile_enable(1)
+        y = wb.dwt(to_gpu(x, dev), wt, L)
+        xr = wb.idwt(y, wt, L)
+        _lib.lib().wb200_profile_enable(0)
+        names = _kernel_names()
+        assert {"walk_filter_analysis", "walk_filter_synthesis"} <= names, names
+        if shape[0] >= 256:
+            assert {"line_filter_analysis", "line_filter_synthesis"} <= names, names
+        check(y, orc.dwt_filter(x, wt.qmf, L), mode, len(shape) * L, 8.0)
+        check(xr, orc.dwt_filter(to_np(y), wt.qmf, L, fw=False), mode, len(shape) * L, 8.0)
+    # batch of images
+    xb = rng(77).standard_normal((128, 128, 3)).astype(dtype)
+    yb = wb.dwtc(to_gpu(xb, dev), wt, 2)
+    check(yb, orc.dwt_filter_batch(xb, 2, wt.qmf, 2), mode, 4, 8.0)
+    check(wb.idwtc(yb, wt, 2), orc.dwt_filter_batch(to_np(yb), 2, wt.qmf, 2, fw=False), mode, 4, 8.0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,B,wname", [(4096, 3, "sym8"), (16384, 2, "db4"), (3 * 4096, 2, "db10"), (64, 5, "haar")])
+def test_fastpass_wpt_full_tree(dev, mode, dtype, n, B, wname):
+    """full packet trees: line kernels while a node exceeds 4096 samples, then one shared-memory subtree launch"""
+    from wavelets_b200 import _lib
+    wf = wavelet(wavelet_class(wname))
+    x = rng(n + B).standard_normal((n, B)).astype(dtype)
+    Lmax = wb.maxtransformlevels(n)
+    for L in (Lmax, max(2, Lmax - 3)):
+        t = wb.maketree(n, L, "full")
+        _lib.lib().wb200_profile_enable(1)
+        y = wb.wpt(to_gpu(x, dev), wf, t)
+        xr = wb.iwpt(y, wf, t)
+        _lib.lib().wb200_profile_enable(0)
+        names = _kernel_names()
+        assert {"wpt_subtree_analysis", "wpt_subtree_synthesis"} <= names, names
+        if n > 4096:
+            assert {"line_filter_analysis", "line_filter_synthesis"} <= names, names
+        yn, xn = to_np(y), to_np(xr)
+        for b in range(B):
+            check(np.ascontiguousarray(yn[:, b]), orc.wpt_filter(x[:, b].copy(), wf.qmf, t), mode, L, 4.0)
+            check(np.ascontiguousarray(xn[:, b]), orc.wpt_filter(yn[:, b].copy(), wf.qmf, t, fw=False), mode, L, 4.0)

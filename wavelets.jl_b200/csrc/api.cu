@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <algorithm>
 #include <vector>
 
 namespace wb {
@@ -316,22 +317,50 @@ static int32_t run_wpt(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t
     if (!W || !dtree) { set_error("internal: WPT workspace plan mismatch"); return WB200_EWORKSPACE; }
     if (!cuda_ok(cudaMemcpyAsync(dtree, tree, (size_t)ntree, cudaMemcpyHostToDevice, op.st), "cudaMemcpyAsync(tree)")) return WB200_ECUDA;
 
+    // Sweeps: one per tree level, except that a run of FULL levels whose nodes fit shared memory is taken by one
+    // subtree launch (filter path).  lv_sub = first level of that run (deep: none).
+    int lv_sub = deep;
+    if (!op.lifting && !op.generic_only && C == 1) {
+        int lv = deep;
+        while (lv > 0) {                       // extend the run upwards while the level is fully active
+            const int64_t nodes = (int64_t)1 << (lv - 1);
+            bool all = true;
+            for (int64_t k = 0; k < nodes; ++k) all = all && tree[(nodes - 1) + k];
+            if (!all || (n >> (lv - 1)) > 4096) break;
+            --lv;
+        }
+        if (deep - lv >= 2) lv_sub = lv;       // worth a dedicated launch only for two or more levels
+    }
+    struct Sweep { int lv, count; };
+    std::vector<Sweep> sweeps;
+    for (int lv = 0; lv < lv_sub; ++lv) sweeps.push_back({lv, 1});
+    if (lv_sub < deep) sweeps.push_back({lv_sub, deep - lv_sub});
+    if (!fw) std::reverse(sweeps.begin(), sweeps.end());
     // sweep i writes D_i; the last sweep must land in y unless that would make sweep 0 in place (x == y)
-    const int ns = deep;
+    const int ns = (int)sweeps.size();
     auto dst_of = [&](int i) -> T * { return ((ns - 1 - i) % 2 == 0) ? y : W; };
     bool flip = (x == y) && (dst_of(0) == y);
     auto dst2 = [&](int i) -> T * { T *d = dst_of(i); return flip ? (d == y ? W : y) : d; };
     const int64_t thr[4] = {0, 0, 0, 0};
     for (int i = 0; i < ns; ++i) {
-        const int lv = fw ? i : ns - 1 - i;
+        const int lv = sweeps[i].lv;
         const int64_t nj = n >> lv, nodes = (int64_t)1 << lv;
         const T *S = (i == 0) ? x : dst2(i - 1);
         T *D = dst2(i);
+        if (sweeps[i].count > 1) {
+            const int r = fast_wpt_subtree<T>(S, D, n, nj, sweeps[i].count, nodes, B, op.fc, op.strict, fw, op.st);
+            if (r < 0) return WB200_ECUDA;
+            if (r > 0) continue;
+            set_error("internal: packet subtree kernel rejected a planned sweep");
+            return WB200_ECUDA;
+        }
         Extent e; e.len = nj; e.n[0] = C; e.n[1] = nodes; e.n[2] = 1; e.n[3] = B;
         View<T> vs, vd;
         vs.p = const_cast<T *>(S); vs.ls = C; vs.s[0] = 1; vs.s[1] = nj * C; vs.s[2] = 0; vs.s[3] = n * C;
         vd = vs; vd.p = D;
-        const uint8_t *act = dtree + (nodes - 1);
+        bool all_active = true;
+        for (int64_t k = 0; k < nodes; ++k) all_active = all_active && tree[(nodes - 1) + k];
+        const uint8_t *act = all_active ? nullptr : dtree + (nodes - 1);   // full levels take the fast line kernels
         const int64_t half = (nj / 2) * C;
         if (fw) {
             if (!op.analysis(cview(vs), vd, offset_view(vd, half), e, act)) return WB200_ECUDA;
@@ -577,11 +606,11 @@ extern "C" int32_t wb200_dwt_filter(void *y, const void *x, int32_t ndim, const 
     if (y == x) { set_error("in array is out array"); return WB200_EALIAS; }
     cudaStream_t st = (cudaStream_t)stream;
     if (c.is_f64) {
-        PassOp<double> op; op.lifting = false; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st;
+        PassOp<double> op; op.lifting = false; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st; op.generic_only = (flags & WB200_FLAG_FORCE_GENERIC) != 0;
         make_filter<double>(op.fc, qmf, flen);
         return dispatch_dwt<double>(op, y, x, c, L, fw != 0, false, workspace, workspace_bytes, st, flags);
     } else {
-        PassOp<float> op; op.lifting = false; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st;
+        PassOp<float> op; op.lifting = false; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st; op.generic_only = (flags & WB200_FLAG_FORCE_GENERIC) != 0;
         make_filter<float>(op.fc, qmf, flen);
         return dispatch_dwt<float>(op, y, x, c, L, fw != 0, false, workspace, workspace_bytes, st, flags);
     }
@@ -604,11 +633,11 @@ extern "C" int32_t wb200_dwt_lifting(void *y, const void *x, int32_t ndim, const
     if (y == nullptr || x == nullptr) { set_error("null array pointer"); return WB200_EARG; }
     cudaStream_t st = (cudaStream_t)stream;
     if (c.is_f64) {
-        PassOp<double> op; op.lifting = true; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st;
+        PassOp<double> op; op.lifting = true; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st; op.generic_only = (flags & WB200_FLAG_FORCE_GENERIC) != 0;
         make_scheme<double>(op.sc, steps, nsteps, norm1, norm2, fw != 0);
         return dispatch_dwt<double>(op, y, x, c, L, fw != 0, true, workspace, workspace_bytes, st, flags);
     } else {
-        PassOp<float> op; op.lifting = true; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st;
+        PassOp<float> op; op.lifting = true; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st; op.generic_only = (flags & WB200_FLAG_FORCE_GENERIC) != 0;
         make_scheme<float>(op.sc, steps, nsteps, norm1, norm2, fw != 0);
         return dispatch_dwt<float>(op, y, x, c, L, fw != 0, true, workspace, workspace_bytes, st, flags);
     }
@@ -643,11 +672,11 @@ extern "C" int32_t wb200_wpt_filter(void *y, const void *x, int64_t n, int64_t b
     if (!isvalidtree(n, tree, ntree)) { set_error("invalid tree"); return WB200_ETREE; }
     cudaStream_t st = (cudaStream_t)stream;
     if (c.is_f64) {
-        PassOp<double> op; op.lifting = false; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st;
+        PassOp<double> op; op.lifting = false; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st; op.generic_only = (flags & WB200_FLAG_FORCE_GENERIC) != 0;
         make_filter<double>(op.fc, qmf, flen);
         return wpt_common<double>(op, y, x, n, c.g.C, batch, tree, ntree, fw != 0, workspace, workspace_bytes, st);
     } else {
-        PassOp<float> op; op.lifting = false; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st;
+        PassOp<float> op; op.lifting = false; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st; op.generic_only = (flags & WB200_FLAG_FORCE_GENERIC) != 0;
         make_filter<float>(op.fc, qmf, flen);
         return wpt_common<float>(op, y, x, n, c.g.C, batch, tree, ntree, fw != 0, workspace, workspace_bytes, st);
     }
@@ -667,11 +696,11 @@ extern "C" int32_t wb200_wpt_lifting(void *y, const void *x, int64_t n, int64_t 
     if (!isvalidtree(n, tree, ntree)) { set_error("invalid tree"); return WB200_ETREE; }
     cudaStream_t st = (cudaStream_t)stream;
     if (c.is_f64) {
-        PassOp<double> op; op.lifting = true; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st;
+        PassOp<double> op; op.lifting = true; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st; op.generic_only = (flags & WB200_FLAG_FORCE_GENERIC) != 0;
         make_scheme<double>(op.sc, steps, nsteps, norm1, norm2, fw != 0);
         return wpt_common<double>(op, y, x, n, c.g.C, batch, tree, ntree, fw != 0, workspace, workspace_bytes, st);
     } else {
-        PassOp<float> op; op.lifting = true; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st;
+        PassOp<float> op; op.lifting = true; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st; op.generic_only = (flags & WB200_FLAG_FORCE_GENERIC) != 0;
         make_scheme<float>(op.sc, steps, nsteps, norm1, norm2, fw != 0);
         return wpt_common<float>(op, y, x, n, c.g.C, batch, tree, ntree, fw != 0, workspace, workspace_bytes, st);
     }

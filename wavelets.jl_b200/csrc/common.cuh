@@ -122,20 +122,43 @@ bool launch_copy_lines(const View<const T> &src, const View<T> &dst, const Exten
 // ---------------------------------------------------------------------------------------------------
 // one-level pass abstraction shared by the filter and lifting drivers
 // ---------------------------------------------------------------------------------------------------
+// fast single-level filter passes (fastpass.cu): 1 = handled, 0 = layout not covered (use the generic pass), -1 = error
+template <typename T>
+int fast_filter_analysis(const View<const T> &src, const View<T> &dlo, const View<T> &dhi, const Extent &e,
+                         const FilterCoefs<T> &fc, bool strict, cudaStream_t st);
+template <typename T>
+int fast_filter_synthesis(const View<const T> &slo, const View<const T> &shi, const View<const T> &salt,
+                          const int64_t thr[4], bool has_alt, const View<T> &dst, const Extent &e,
+                          const FilterCoefs<T> &fc, bool strict, cudaStream_t st);
+
+// whole packet subtrees in shared memory (fastpass.cu): every node of m samples goes through `levels` full levels
+template <typename T>
+int fast_wpt_subtree(const T *S, T *D, int64_t n, int64_t m, int levels, int64_t nodes, int64_t B,
+                     const FilterCoefs<T> &fc, bool strict, bool fw, cudaStream_t st);
+
 template <typename T> struct PassOp {
     bool lifting;
     bool strict;
     cudaStream_t st;
     FilterCoefs<T> fc;
     LiftScheme<T> sc;
+    bool generic_only = false;
     bool analysis(const View<const T> &src, const View<T> &dlo, const View<T> &dhi, const Extent &e,
                   const uint8_t *active = nullptr) const {
+        if (!lifting && !generic_only && active == nullptr) {
+            const int r = fast_filter_analysis<T>(src, dlo, dhi, e, fc, strict, st);
+            if (r != 0) return r > 0;
+        }
         return lifting ? launch_lifting_analysis<T>(src, dlo, dhi, e, sc, strict, st, active)
                        : launch_filter_analysis<T>(src, dlo, dhi, e, fc, strict, st, active);
     }
     bool synthesis(const View<const T> &slo, const View<const T> &shi, const View<const T> &salt,
                    const int64_t thr[4], bool has_alt, const View<T> &dst, const Extent &e,
                    const uint8_t *active = nullptr) const {
+        if (!lifting && !generic_only && active == nullptr) {
+            const int r = fast_filter_synthesis<T>(slo, shi, salt, thr, has_alt, dst, e, fc, strict, st);
+            if (r != 0) return r > 0;
+        }
         return lifting ? launch_lifting_synthesis<T>(slo, shi, salt, thr, has_alt, dst, e, sc, strict, st, active)
                        : launch_filter_synthesis<T>(slo, shi, salt, thr, has_alt, dst, e, fc, strict, st, active);
     }

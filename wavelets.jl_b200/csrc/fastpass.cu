@@ -1,0 +1,516 @@
+// fastpass.cu -- fast single-level filter-bank passes for the N-D and wavelet-packet drivers (sm_100a).
+//
+// The N-D drivers (api.cu run_nd) and the packet driver (run_wpt) work one level and one dimension at a time.
+// Two kernel families replace the generic one-thread-per-output pass where the layout allows it:
+//
+//   line kernels  (k_line_ana / k_line_syn): the lines are CONTIGUOUS (dim-1 pass of an N-D level, packet nodes).
+//       Same machinery as the fused 1-D tiles with K = 1: a CTA stages TILE (+halo) samples of one line with a TMA
+//       bulk copy (second copy for the periodic wrap), computes approximation + detail from 128-bit shared-memory
+//       windows and streams both halves out with 64/128-bit stores.
+//   walk kernels  (k_walk_ana / k_walk_syn): the lines are STRIDED and another coordinate is contiguous (dim-2 /
+//       dim-3 passes).  Threads run along the contiguous coordinate (every load and store is a coalesced 128-byte
+//       row), each thread holds a short run of its line in registers (2*RK + F - 2 samples, all loads issued up
+//       front) and emits RK approximation/detail pairs.  No shared memory, no transposes.
+//
+// Arithmetic: the closed forms of filtdown!/filtup! in the reference's summation order; the detail
+// is produced from the same window as the approximation (d[k + F/2 - 1] and a[k] read the same F inputs).
+#include "fused1d_dev.cuh"
+
+namespace wb {
+
+static int env_fast_enabled() {
+    const char *v = getenv("WB200_DISABLE_FASTPASS");
+    return (v && *v && atoi(v)) ? 0 : 1;
+}
+
+struct LineCoord { int64_t c0, c1, c2, c3; };
+__device__ __forceinline__ LineCoord split_line(int64_t ln, const Extent &e) {
+    LineCoord c;
+    c.c0 = ln % e.n[0]; ln /= e.n[0];
+    c.c1 = ln % e.n[1]; ln /= e.n[1];
+    c.c2 = ln % e.n[2];
+    c.c3 = ln / e.n[2];
+    return c;
+}
+
+// ===================================================================================================
+// contiguous lines: one level per launch out of TMA-staged tiles
+// ===================================================================================================
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(256)
+k_line_ana(View<const T> src, View<T> dlo, View<T> dhi, Extent e, int tile, int h0, int ntiles,
+           const __grid_constant__ Taps<T, F> c) {
+    constexpr int PA = AnaPairs<T>::value;
+    using G = FGeom<F, PA>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    T *buf = reinterpret_cast<T *>(smem_raw + 128);
+    const int64_t bid = blockIdx.x;
+    const int64_t ln = bid / ntiles;
+    const int t = (int)(bid - ln * ntiles);
+    const LineCoord lc = split_line(ln, e);
+    const T *x = src.line(lc.c0, lc.c1, lc.c2, lc.c3);
+    T *lo = dlo.line(lc.c0, lc.c1, lc.c2, lc.c3);
+    T *hi = dhi.line(lc.c0, lc.c1, lc.c2, lc.c3);
+    const int64_t n = e.len, nh = n >> 1;
+    const int64_t s = (int64_t)t * tile, sl = s >> 1;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)((tile + h0) * sizeof(T)));
+        tma_load_wrapped<T>(buf, x, s, tile + h0, n, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const int ND = tile >> 1;
+    T *dbase = hi + sl + G::DS;
+    const int64_t room = nh - sl - G::DS;
+    const int wrap_at = room < (int64_t)ND ? (int)room : 0x7fffffff;
+    const int wrap_by = (int)nh;
+    auto store_d = [&](int p, const T (&d)[PA]) {
+        T *q = dbase + (p >= wrap_at ? p - wrap_by : p);
+        if constexpr (PA == 2) gstore2(q, d[0], d[1]); else __stcs(q, d[0]);
+    };
+    T *abase = lo + sl;
+    auto store_a = [&](int p, const T (&a)[PA]) {
+        if constexpr (PA == 2) gstore2(abase + p, a[0], a[1]); else __stcs(abase + p, a[0]);
+    };
+    ana_level<T, F, STRICT>(buf, ND, ND, c, store_a, store_d);
+}
+
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(256)
+k_line_syn(View<const T> slo, View<const T> shi, View<const T> salt, int64_t thr0, int64_t thr1, int64_t thr2, int64_t thr3,
+           int has_alt, View<T> dst, Extent e, int ntiles, const __grid_constant__ Taps<T, F> c,
+           const __grid_constant__ SynPlan pl) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    T *sm = reinterpret_cast<T *>(smem_raw + 128);
+    const int64_t bid = blockIdx.x;
+    const int64_t ln = bid / ntiles;
+    const int t = (int)(bid - ln * ntiles);
+    const LineCoord lc = split_line(ln, e);
+    const bool alt = has_alt && lc.c0 < thr0 && lc.c1 < thr1 && lc.c2 < thr2 && lc.c3 < thr3;
+    const T *a = alt ? salt.line(lc.c0, lc.c1, lc.c2, lc.c3) : slo.line(lc.c0, lc.c1, lc.c2, lc.c3);
+    const T *d = shi.line(lc.c0, lc.c1, lc.c2, lc.c3);
+    T *o = dst.line(lc.c0, lc.c1, lc.c2, lc.c3);
+    const int64_t nh = e.len >> 1;
+    const int64_t s = (int64_t)t * pl.tile;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (uint32_t)(((pl.rhi[1] - pl.rlo[1]) + (pl.dhi[1] - pl.dlo[1])) * sizeof(T)));
+        tma_load_wrapped<T>(sm + pl.aoff, a, (s >> 1) + pl.rlo[1], pl.rhi[1] - pl.rlo[1], nh, bar);
+        tma_load_wrapped<T>(sm + pl.doff[1], d, (s >> 1) + pl.dlo[1], pl.dhi[1] - pl.dlo[1], nh, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const int npairs = pl.tile >> 1;
+    const int oa = 0 - pl.rlo[1];
+    const int od = 0 - pl.dlo[1];
+    T *ob = o + s;
+    auto so = [&](int ur, T o0, T o1, T o2, T o3) { gstore4(ob + 2 * ur, o0, o1, o2, o3); };
+    syn_level<T, F, STRICT>(sm + pl.aoff, sm + pl.doff[1], oa, od, npairs, c, so);
+}
+
+// ===================================================================================================
+// strided lines: register runs, coalesced across the contiguous coordinate
+// ===================================================================================================
+template <int F> struct WalkCfg { static constexpr int RK = F <= 12 ? 16 : 8; };
+
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(128)
+k_walk_ana(View<const T> src, View<T> dlo, View<T> dhi, Extent e, int nseg, const __grid_constant__ Taps<T, F> c) {
+    using fp = FP<STRICT>;
+    constexpr int RK = WalkCfg<F>::RK;
+    constexpr int W = 2 * RK + F - 2;
+    constexpr int DS = F / 2 - 1;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= e.n[0]) return;
+    const int seg = blockIdx.y % nseg;
+    const int64_t yy = blockIdx.y / nseg + (int64_t)blockIdx.z * (gridDim.y / nseg);
+    const int64_t NY = e.n[1] * e.n[2] * e.n[3];
+    if (yy >= NY) return;
+    const int64_t c1 = yy % e.n[1], r = yy / e.n[1], c2 = r % e.n[2], c3 = r / e.n[2];
+    const T *x = src.line(i0, c1, c2, c3);
+    T *lo = dlo.line(i0, c1, c2, c3);
+    T *hi = dhi.line(i0, c1, c2, c3);
+    const int64_t n = e.len, nh = n >> 1;
+    const int64_t k0 = (int64_t)seg * RK;
+    T w[W];
+    {
+        int64_t idx = (2 * k0) % n;
+#pragma unroll
+        for (int m = 0; m < W; ++m) {
+            w[m] = x[idx * src.ls];
+            if (++idx == n) idx = 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RK; ++k) {
+        if (k0 + k < nh) {
+            T a = fp::mul(c.h[0], w[2 * k]);
+            T d = fp::mul(c.g[F - 1], w[2 * k]);
+#pragma unroll
+            for (int m = 1; m < F; ++m) {
+                a = fp::mac(a, c.h[m], w[2 * k + m]);
+                d = fp::mac(d, c.g[F - 1 - m], w[2 * k + m]);
+            }
+            lo[(k0 + k) * dlo.ls] = a;
+            const int64_t kd = (k0 + k + DS) % nh;
+            hi[kd * dhi.ls] = d;
+        }
+    }
+}
+
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(128)
+k_walk_syn(View<const T> slo, View<const T> shi, View<const T> salt, int64_t thr0, int64_t thr1, int64_t thr2, int64_t thr3,
+           int has_alt, View<T> dst, Extent e, int nseg, const __grid_constant__ Taps<T, F> c) {
+    using fp = FP<STRICT>;
+    constexpr int RK = WalkCfg<F>::RK;
+    constexpr int Q = F / 2;
+    constexpr int W = RK + Q - 1;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= e.n[0]) return;
+    const int seg = blockIdx.y % nseg;
+    const int64_t yy = blockIdx.y / nseg + (int64_t)blockIdx.z * (gridDim.y / nseg);
+    const int64_t NY = e.n[1] * e.n[2] * e.n[3];
+    if (yy >= NY) return;
+    const int64_t c1 = yy % e.n[1], r = yy / e.n[1], c2 = r % e.n[2], c3 = r / e.n[2];
+    const bool alt = has_alt && i0 < thr0 && c1 < thr1 && c2 < thr2 && c3 < thr3;
+    const T *a;
+    int64_t als;
+    if (alt) { a = salt.line(i0, c1, c2, c3); als = salt.ls; } else { a = slo.line(i0, c1, c2, c3); als = slo.ls; }
+    const T *d = shi.line(i0, c1, c2, c3);
+    T *o = dst.line(i0, c1, c2, c3);
+    const int64_t nh = e.len >> 1;
+    const int64_t u0 = (int64_t)seg * RK;
+    // wa[i] = a[(u0 - Q + 1 + i) mod nh], wd[i] = d[(u0 + i) mod nh]
+    T wa[W], wd[W];
+    {
+        int64_t ia = (u0 - (Q - 1)) % nh;
+        if (ia < 0) ia += nh;
+        int64_t id = u0 % nh;
+#pragma unroll
+        for (int i = 0; i < W; ++i) {
+            wa[i] = a[ia * als];
+            wd[i] = d[id * shi.ls];
+            if (++ia == nh) ia = 0;
+            if (++id == nh) id = 0;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RK; ++k) {
+        if (u0 + k < nh) {
+            // a[u - j] = wa[k + Q - 1 - j], d[u + j] = wd[k + j]
+            T rae = fp::mul(c.h[2 * (Q - 1)], wa[k]);
+            T rao = fp::mul(c.h[2 * (Q - 1) + 1], wa[k]);
+#pragma unroll
+            for (int j = Q - 2; j >= 0; --j) {
+                rae = fp::mac(rae, c.h[2 * j], wa[k + Q - 1 - j]);
+                rao = fp::mac(rao, c.h[2 * j + 1], wa[k + Q - 1 - j]);
+            }
+            T rde = fp::mul(c.g[1], wd[k]);
+            T rdo = fp::mul(c.g[0], wd[k]);
+#pragma unroll
+            for (int j = 1; j < Q; ++j) {
+                rde = fp::mac(rde, c.g[2 * j + 1], wd[k + j]);
+                rdo = fp::mac(rdo, c.g[2 * j], wd[k + j]);
+            }
+            o[(2 * (u0 + k)) * dst.ls] = fp::add(rae, rde);
+            o[(2 * (u0 + k) + 1) * dst.ls] = fp::add(rao, rdo);
+        }
+    }
+}
+
+// ===================================================================================================
+// wavelet-packet subtrees: a node of <= WPT_SUB_MAX samples is decomposed (or rebuilt) through ALL of its
+// remaining full levels by one CTA in shared memory -- one launch instead of one per level, one HBM read and one
+// write of the node.  Sub-node j of level l occupies [j*ml, (j+1)*ml) of the node's span and is replaced in place by
+// [approximation | detail] (natural / Paley order, transforms_filter.jl:337-353).
+// ===================================================================================================
+constexpr int WPT_SUB_MAX = 4096;
+
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(256)
+k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int levels, int64_t nodes,
+              const __grid_constant__ Taps<T, F> c) {
+    using fp = FP<STRICT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *in = reinterpret_cast<T *>(smem_raw);
+    T *out = in + m;
+    const int64_t q = blockIdx.x % nodes, b = blockIdx.x / nodes;
+    const int64_t base = b * n + q * (int64_t)m;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) in[i] = S[base + i];
+    __syncthreads();
+    for (int l = 0; l < levels; ++l) {
+        const int ml = m >> l, nh = ml >> 1;
+        for (int idx = threadIdx.x; idx < (m >> 1); idx += blockDim.x) {
+            const int j = idx / nh, k = idx - j * nh;
+            const T *x = in + j * ml;
+            int ia = 2 * k;
+            T a = fp::mul(c.h[0], x[ia]);
+#pragma unroll
+            for (int t = 1; t < F; ++t) {
+                if (++ia == ml) ia = 0;
+                a = fp::mac(a, c.h[t], x[ia]);
+            }
+            int id = (2 * k + 2 - F) % ml;
+            if (id < 0) id += ml;
+            T d = fp::mul(c.g[F - 1], x[id]);
+#pragma unroll
+            for (int t = 1; t < F; ++t) {
+                if (++id == ml) id = 0;
+                d = fp::mac(d, c.g[F - 1 - t], x[id]);
+            }
+            out[j * ml + k] = a;
+            out[j * ml + nh + k] = d;
+        }
+        __syncthreads();
+        T *t = in; in = out; out = t;
+    }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) D[base + i] = in[i];
+}
+
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(256)
+k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int levels, int64_t nodes,
+              const __grid_constant__ Taps<T, F> c) {
+    using fp = FP<STRICT>;
+    constexpr int Q = F / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *in = reinterpret_cast<T *>(smem_raw);
+    T *out = in + m;
+    const int64_t q = blockIdx.x % nodes, b = blockIdx.x / nodes;
+    const int64_t base = b * n + q * (int64_t)m;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) in[i] = S[base + i];
+    __syncthreads();
+    for (int l = levels - 1; l >= 0; --l) {
+        const int ml = m >> l, nh = ml >> 1;
+        for (int idx = threadIdx.x; idx < (m >> 1); idx += blockDim.x) {
+            const int j = idx / nh, u = idx - j * nh;
+            const T *a = in + j * ml, *d = a + nh;
+            int ia = (u - (Q - 1)) % nh;
+            if (ia < 0) ia += nh;
+            T rae = fp::mul(c.h[2 * (Q - 1)], a[ia]);
+            T rao = fp::mul(c.h[2 * (Q - 1) + 1], a[ia]);
+#pragma unroll
+            for (int t = Q - 2; t >= 0; --t) {
+                if (++ia == nh) ia = 0;
+                rae = fp::mac(rae, c.h[2 * t], a[ia]);
+                rao = fp::mac(rao, c.h[2 * t + 1], a[ia]);
+            }
+            int id = u;
+            T rde = fp::mul(c.g[1], d[id]);
+            T rdo = fp::mul(c.g[0], d[id]);
+#pragma unroll
+            for (int t = 1; t < Q; ++t) {
+                if (++id == nh) id = 0;
+                rde = fp::mac(rde, c.g[2 * t + 1], d[id]);
+                rdo = fp::mac(rdo, c.g[2 * t], d[id]);
+            }
+            out[j * ml + 2 * u] = fp::add(rae, rde);
+            out[j * ml + 2 * u + 1] = fp::add(rao, rdo);
+        }
+        __syncthreads();
+        T *t = in; in = out; out = t;
+    }
+    for (int i = threadIdx.x; i < m; i += blockDim.x) D[base + i] = in[i];
+}
+
+template <typename T, int F, bool STRICT>
+static int wpt_sub_F(const T *S, T *D, int64_t n, int m, int levels, int64_t nodes, int64_t B, const FilterCoefs<T> &fc,
+                     bool fw, cudaStream_t st) {
+    Taps<T, F> taps;
+    for (int k = 0; k < F; ++k) { taps.h[k] = fc.h[k]; taps.g[k] = fc.g[k]; }
+    const int64_t nblk = nodes * B;
+    if (nblk > 0x7fffffffLL) return 0;
+    const size_t smem = (size_t)2 * m * sizeof(T);
+    if (fw) {
+        auto kern = k_wpt_sub_ana<T, F, STRICT>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+        LaunchScope scope("wpt_subtree_analysis", st);
+        kern<<<(unsigned)nblk, 256, smem, st>>>(S, D, n, m, levels, nodes, taps);
+    } else {
+        auto kern = k_wpt_sub_syn<T, F, STRICT>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+        LaunchScope scope("wpt_subtree_synthesis", st);
+        kern<<<(unsigned)nblk, 256, smem, st>>>(S, D, n, m, levels, nodes, taps);
+    }
+    return check_launch("wpt_subtree") ? 1 : -1;
+}
+
+// nodes of m samples each (m <= WPT_SUB_MAX, m % 2^levels == 0), `levels` full levels; 1 handled / 0 not covered / -1 error
+template <typename T>
+int fast_wpt_subtree(const T *S, T *D, int64_t n, int64_t m, int levels, int64_t nodes, int64_t B,
+                     const FilterCoefs<T> &fc, bool strict, bool fw, cudaStream_t st) {
+    if (!env_fast_enabled() || m > WPT_SUB_MAX || m < 2 || levels < 1 || (m % ((int64_t)1 << levels)) != 0) return 0;
+    switch (fc.F) {
+#define WB_CASE(FF) case FF: return strict ? wpt_sub_F<T, FF, true>(S, D, n, (int)m, levels, nodes, B, fc, fw, st) : wpt_sub_F<T, FF, false>(S, D, n, (int)m, levels, nodes, B, fc, fw, st);
+        WB_CASE(2) WB_CASE(4) WB_CASE(6) WB_CASE(8) WB_CASE(10) WB_CASE(12) WB_CASE(14) WB_CASE(16) WB_CASE(18) WB_CASE(20)
+#undef WB_CASE
+    default: return 0;
+    }
+}
+
+// ===================================================================================================
+// host dispatch
+// ===================================================================================================
+template <typename T> static bool aligned16_view(const View<T> &v, const Extent &e) {
+    if ((reinterpret_cast<uintptr_t>(v.p) & 15) != 0) return false;
+    for (int q = 0; q < 4; ++q)
+        if (e.n[q] > 1 && ((v.s[q] * (int64_t)sizeof(T)) % 16) != 0) return false;
+    return true;
+}
+static int pick_line_tile(int64_t len, int esize, bool whole_line_ok) {
+    int64_t tile = esize == 4 ? 8192 : 4096;
+    const int64_t p2 = len & (-len);
+    while (tile > p2) tile >>= 1;
+    // analysis may take the whole line as one tile (the wrap piece is the start of the same line); synthesis stages
+    // ranges a little longer than half a tile and needs them to fit the half-length bands: at least two tiles per line
+    while (tile > (whole_line_ok ? len : len / 2)) tile >>= 1;
+    return (int)tile;
+}
+
+template <typename T, int F, bool STRICT>
+static int fast_ana_F(const View<const T> &src, const View<T> &dlo, const View<T> &dhi, const Extent &e,
+                      const FilterCoefs<T> &fc, cudaStream_t st) {
+    Taps<T, F> taps;
+    for (int m = 0; m < F; ++m) { taps.h[m] = fc.h[m]; taps.g[m] = fc.g[m]; }
+    const int64_t NL = e.n[0] * e.n[1] * e.n[2] * e.n[3];
+    if (NL <= 0 || e.len < 2) return 1;
+    if (src.ls == 1 && dlo.ls == 1 && dhi.ls == 1) {
+        // ---- contiguous lines ----
+        constexpr int PA = AnaPairs<T>::value;
+        using G = FGeom<F, PA>;
+        const int tile = pick_line_tile(e.len, sizeof(T), true);
+        const int vec = 16 / (int)sizeof(T);
+        const int h0 = (F - 2 + G::WO + vec - 1) / vec * vec;
+        if (tile < 64 || h0 > tile || (e.len * (int64_t)sizeof(T)) % 16 != 0 || e.len > ((int64_t)1 << 30)) return 0;
+        if (!aligned16_view(src, e) || !aligned16_view(View<const T>{dlo.p, dlo.ls, {dlo.s[0], dlo.s[1], dlo.s[2], dlo.s[3]}}, e) ||
+            !aligned16_view(View<const T>{dhi.p, dhi.ls, {dhi.s[0], dhi.s[1], dhi.s[2], dhi.s[3]}}, e)) return 0;
+        const int64_t ntiles = e.len / tile;
+        const int64_t nblk = ntiles * NL;
+        if (nblk > 0x7fffffffLL) return 0;
+        const size_t smem = 128 + (size_t)(tile + h0 + 8) * sizeof(T);
+        auto kern = k_line_ana<T, F, STRICT>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+        {
+            LaunchScope scope("line_filter_analysis", st);
+            const int nthr = tile >= 1024 ? 256 : (tile >= 512 ? 128 : 64);
+            kern<<<(unsigned)nblk, nthr, smem, st>>>(src, dlo, dhi, e, tile, h0, (int)ntiles, taps);
+        }
+        return check_launch("line_filter_analysis") ? 1 : -1;
+    }
+    if (src.s[0] == 1 && dlo.s[0] == 1 && dhi.s[0] == 1 && e.n[0] >= 16) {
+        // ---- strided lines, contiguous coordinate 0 ----
+        constexpr int RK = WalkCfg<F>::RK;
+        const int64_t nh = e.len / 2;
+        const int64_t nseg = (nh + RK - 1) / RK;
+        const int64_t NY = e.n[1] * e.n[2] * e.n[3];
+        int64_t gy = nseg * NY, gz = 1;
+        if (nseg > 65535) return 0;
+        if (gy > 65535) { const int64_t per = 65535 / nseg; gz = (NY + per - 1) / per; gy = per * nseg; if (gz > 65535) return 0; }
+        dim3 grid((unsigned)((e.n[0] + 127) / 128), (unsigned)gy, (unsigned)gz);
+        {
+            LaunchScope scope("walk_filter_analysis", st);
+            k_walk_ana<T, F, STRICT><<<grid, 128, 0, st>>>(src, dlo, dhi, e, (int)nseg, taps);
+        }
+        return check_launch("walk_filter_analysis") ? 1 : -1;
+    }
+    return 0;
+}
+
+template <typename T, int F, bool STRICT>
+static int fast_syn_F(const View<const T> &slo, const View<const T> &shi, const View<const T> &salt, const int64_t thr[4],
+                      bool has_alt, const View<T> &dst, const Extent &e, const FilterCoefs<T> &fc, cudaStream_t st) {
+    Taps<T, F> taps;
+    for (int m = 0; m < F; ++m) { taps.h[m] = fc.h[m]; taps.g[m] = fc.g[m]; }
+    const int64_t NL = e.n[0] * e.n[1] * e.n[2] * e.n[3];
+    if (NL <= 0 || e.len < 2) return 1;
+    if (slo.ls == 1 && shi.ls == 1 && dst.ls == 1 && (!has_alt || salt.ls == 1)) {
+        using G = FGeom<F>;
+        const int tile = pick_line_tile(e.len, sizeof(T), false);
+        if (tile < 64 || (e.len * (int64_t)sizeof(T)) % 32 != 0 || e.len > ((int64_t)1 << 30)) return 0;
+        if (!aligned16_view(slo, e) || !aligned16_view(shi, e) || (has_alt && !aligned16_view(salt, e)) ||
+            !aligned16_view(View<const T>{dst.p, dst.ls, {dst.s[0], dst.s[1], dst.s[2], dst.s[3]}}, e)) return 0;
+        auto dn4 = [](int v) { return (v >= 0) ? (v & ~3) : -(((-v) + 3) & ~3); };
+        auto up4 = [](int v) { return (v + 3) & ~3; };
+        SynPlan pl;
+        memset(&pl, 0, sizeof(pl));
+        pl.K = 1; pl.tile = tile;
+        pl.rlo[0] = 0; pl.rhi[0] = tile;
+        pl.rlo[1] = dn4(-G::QA); pl.rhi[1] = tile / 2;
+        pl.dlo[1] = 0; pl.dhi[1] = up4(tile / 2 + G::QD - 2);
+        pl.doff[1] = 0;
+        pl.aoff = pl.dhi[1] - pl.dlo[1];
+        const int64_t nh = e.len / 2;
+        if ((int64_t)(pl.dhi[1] - pl.dlo[1]) > nh || (int64_t)(pl.rhi[1] - pl.rlo[1]) > nh) return 0;
+        const size_t smem = 128 + (size_t)(pl.aoff + (pl.rhi[1] - pl.rlo[1]) + 8) * sizeof(T);
+        const int64_t ntiles = e.len / tile;
+        const int64_t nblk = ntiles * NL;
+        if (nblk > 0x7fffffffLL) return 0;
+        auto kern = k_line_syn<T, F, STRICT>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+        {
+            LaunchScope scope("line_filter_synthesis", st);
+            const int nthr = tile >= 1024 ? 256 : (tile >= 512 ? 128 : 64);
+            kern<<<(unsigned)nblk, nthr, smem, st>>>(slo, shi, salt, thr[0], thr[1], thr[2], thr[3], has_alt ? 1 : 0, dst, e, (int)ntiles, taps, pl);
+        }
+        return check_launch("line_filter_synthesis") ? 1 : -1;
+    }
+    if (slo.s[0] == 1 && shi.s[0] == 1 && dst.s[0] == 1 && (!has_alt || salt.s[0] == 1) && e.n[0] >= 16) {
+        constexpr int RK = WalkCfg<F>::RK;
+        const int64_t nh = e.len / 2;
+        const int64_t nseg = (nh + RK - 1) / RK;
+        const int64_t NY = e.n[1] * e.n[2] * e.n[3];
+        int64_t gy = nseg * NY, gz = 1;
+        if (nseg > 65535) return 0;
+        if (gy > 65535) { const int64_t per = 65535 / nseg; gz = (NY + per - 1) / per; gy = per * nseg; if (gz > 65535) return 0; }
+        dim3 grid((unsigned)((e.n[0] + 127) / 128), (unsigned)gy, (unsigned)gz);
+        {
+            LaunchScope scope("walk_filter_synthesis", st);
+            k_walk_syn<T, F, STRICT><<<grid, 128, 0, st>>>(slo, shi, salt, thr[0], thr[1], thr[2], thr[3], has_alt ? 1 : 0, dst, e, (int)nseg, taps);
+        }
+        return check_launch("walk_filter_synthesis") ? 1 : -1;
+    }
+    return 0;
+}
+
+
+template <typename T>
+int fast_filter_analysis(const View<const T> &src, const View<T> &dlo, const View<T> &dhi, const Extent &e,
+                         const FilterCoefs<T> &fc, bool strict, cudaStream_t st) {
+    if (!env_fast_enabled()) return 0;
+    switch (fc.F) {
+#define WB_CASE(FF) case FF: return strict ? fast_ana_F<T, FF, true>(src, dlo, dhi, e, fc, st) : fast_ana_F<T, FF, false>(src, dlo, dhi, e, fc, st);
+        WB_CASE(2) WB_CASE(4) WB_CASE(6) WB_CASE(8) WB_CASE(10) WB_CASE(12) WB_CASE(14) WB_CASE(16) WB_CASE(18) WB_CASE(20)
+#undef WB_CASE
+    default: return 0;
+    }
+}
+template <typename T>
+int fast_filter_synthesis(const View<const T> &slo, const View<const T> &shi, const View<const T> &salt,
+                          const int64_t thr[4], bool has_alt, const View<T> &dst, const Extent &e,
+                          const FilterCoefs<T> &fc, bool strict, cudaStream_t st) {
+    if (!env_fast_enabled()) return 0;
+    switch (fc.F) {
+#define WB_CASE(FF) case FF: return strict ? fast_syn_F<T, FF, true>(slo, shi, salt, thr, has_alt, dst, e, fc, st) : fast_syn_F<T, FF, false>(slo, shi, salt, thr, has_alt, dst, e, fc, st);
+        WB_CASE(2) WB_CASE(4) WB_CASE(6) WB_CASE(8) WB_CASE(10) WB_CASE(12) WB_CASE(14) WB_CASE(16) WB_CASE(18) WB_CASE(20)
+#undef WB_CASE
+    default: return 0;
+    }
+}
+
+#define WB_INST(T)                                                                                                    \
+    template int fast_wpt_subtree<T>(const T *, T *, int64_t, int64_t, int, int64_t, int64_t, const FilterCoefs<T> &,  \
+                                     bool, bool, cudaStream_t);                                                       \
+    template int fast_filter_analysis<T>(const View<const T> &, const View<T> &, const View<T> &, const Extent &,      \
+                                         const FilterCoefs<T> &, bool, cudaStream_t);                                 \
+    template int fast_filter_synthesis<T>(const View<const T> &, const View<const T> &, const View<const T> &,        \
+                                          const int64_t[4], bool, const View<T> &, const Extent &,                    \
+                                          const FilterCoefs<T> &, bool, cudaStream_t);
+WB_INST(float)
+WB_INST(double)
+#undef WB_INST
+
+} // namespace wb

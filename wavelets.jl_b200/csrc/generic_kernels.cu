@@ -374,10 +374,19 @@ static inline bool grid_for(const Extent &e, int64_t per_line, dim3 &grid, dim3 
     return true;
 }
 
+// Short lines with a trivial coordinate 0 (packet nodes, late levels): the x dimension of the grid only spans
+// (position, coordinate 0), so fold coordinate 1 into coordinate 0 to keep whole CTAs busy.
+template <typename VT> static inline void swap_slots01(VT &v) { const int64_t t = v.s[0]; v.s[0] = v.s[1]; v.s[1] = t; }
+static inline bool want_swap(const Extent &e, const uint8_t *active) {
+    return active == nullptr && e.n[0] == 1 && e.n[1] > 1 && e.len < 1024;
+}
+
 template <typename T>
-bool launch_filter_analysis(const View<const T> &src, const View<T> &dlo, const View<T> &dhi,
-                            const Extent &e, const FilterCoefs<T> &fc, bool strict, cudaStream_t st,
+bool launch_filter_analysis(const View<const T> &src_, const View<T> &dlo_, const View<T> &dhi_,
+                            const Extent &e_, const FilterCoefs<T> &fc, bool strict, cudaStream_t st,
                             const uint8_t *active) {
+    View<const T> src = src_; View<T> dlo = dlo_, dhi = dhi_; Extent e = e_;
+    if (want_swap(e, active)) { swap_slots01(src); swap_slots01(dlo); swap_slots01(dhi); e.n[0] = e.n[1]; e.n[1] = 1; }
     dim3 grid, block;
     if (!grid_for(e, e.len / 2, grid, block)) return true; // nothing to do
     const bool kfast = (src.ls == 1) || e.n[0] == 1;
@@ -390,10 +399,17 @@ bool launch_filter_analysis(const View<const T> &src, const View<T> &dlo, const 
 }
 
 template <typename T>
-bool launch_filter_synthesis(const View<const T> &slo, const View<const T> &shi, const View<const T> &salt,
-                             const int64_t thr[4], bool has_alt, const View<T> &dst,
-                             const Extent &e, const FilterCoefs<T> &fc, bool strict, cudaStream_t st,
+bool launch_filter_synthesis(const View<const T> &slo_, const View<const T> &shi_, const View<const T> &salt_,
+                             const int64_t thr_[4], bool has_alt, const View<T> &dst_,
+                             const Extent &e_, const FilterCoefs<T> &fc, bool strict, cudaStream_t st,
                              const uint8_t *active) {
+    View<const T> slo = slo_, shi = shi_, salt = salt_; View<T> dst = dst_; Extent e = e_;
+    int64_t thr[4] = {thr_[0], thr_[1], thr_[2], thr_[3]};
+    if (want_swap(e, active)) {
+        swap_slots01(slo); swap_slots01(shi); swap_slots01(salt); swap_slots01(dst);
+        e.n[0] = e.n[1]; e.n[1] = 1;
+        const int64_t t = thr[0]; thr[0] = thr[1]; thr[1] = t;
+    }
     dim3 grid, block;
     if (!grid_for(e, e.len / 2, grid, block)) return true;
     const bool kfast = (dst.ls == 1) || e.n[0] == 1;
