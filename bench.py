@@ -351,50 +351,57 @@ def main():
 
 
 def run_extras(L, wb, _lib, dev, stream, args):
-    """2-D cdf97 lifting 4096^2 Float32 L=8 (configs[2]; a batch of images so the working set exceeds L2) and the
-    1-D workload in the other precision.  Same timing method, fewer steps."""
-    import numpy as np
+    """Secondary workloads of BASELINE.json (reported next to the headline, same CUDA-event timing, fewer steps):
+    configs[2] 2-D cdf97 lifting 4096^2 Float32 L=8 (a batch of 16 images so that the working set exceeds L2),
+    configs[4] 2-D db4 filter bank on the same batch and 3-D db6 512^3 (L=3, the level count of the reference's own
+    3-D benchmarks), configs[3] full wavelet-packet tree sym8 N=2^16 (batch 1024).  Fractions are of the measured HBM
+    peak with the compulsory byte model (2*sizeof(T) per sample per direction)."""
     import torch
-    sp = C.c_void_p(stream.cuda_stream)
-    res = {}
-    wl = wb.wavelet(wb.WT.cdf97, wb.WT.Lifting)
-    steps_arr, ns = _lib.make_steps(wl)
-    n2, Bi = 4096, 16
-    d2 = _lib.dims_array([n2, n2])
-    xi = torch.randn((Bi, n2, n2), dtype=torch.float32, device=dev)
-    yi = torch.empty_like(xi)
-    wsb = L.wb200_workspace_bytes(1, 2, d2, Bi, 8, _lib.F32, 0)
-    wsi = torch.empty(max(wsb, 256), dtype=torch.uint8, device=dev)
-
-    def step2():
-        rc = L.wb200_dwt_lifting(yi.data_ptr(), xi.data_ptr(), 2, d2, Bi, steps_arr, ns, wl.norm1, wl.norm2, 8, 1,
-                                 _lib.F32, wsi.data_ptr(), wsb, sp, 0)
-        assert rc == 0, L.wb200_last_error_string()
-        rc = L.wb200_dwt_lifting(xi.data_ptr(), yi.data_ptr(), 2, d2, Bi, steps_arr, ns, wl.norm1, wl.norm2, 8, 0,
-                                 _lib.F32, wsi.data_ptr(), wsb, sp, 0)
-        assert rc == 0, L.wb200_last_error_string()
-    for _ in range(3):
-        step2()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k = max(3, min(args.steps, 10))
-    e0.record(stream)
-    for _ in range(k):
-        step2()
-    e1.record(stream)
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / k
-    samples = n2 * n2 * Bi
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    gbs = 16.0 * samples / (ms * 1e-3) / 1e9
-    res["dwt2_cdf97_4096x4096_f32_L8"] = {"msamples_per_s_pair": samples / (ms * 1e-3) / 1e6, "images": Bi,
-                                          "ms_per_pair": ms, "achieved_gbs_pair": gbs, "frac_of_hbm_peak": gbs / peak}
-    del xi, yi, wsi
+    k = max(3, min(args.steps, 5))
+
+    def timed_pair(fwd, inv):
+        for _ in range(2):
+            inv(fwd())
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            inv(fwd())
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / k
+
+    def entry(samples, esz, ms, **kw):
+        gbs = 4.0 * esz * samples / (ms * 1e-3) / 1e9
+        d = {"msamples_per_s_pair": samples / (ms * 1e-3) / 1e6, "ms_per_pair": ms, "achieved_gbs_pair": gbs,
+             "frac_of_hbm_peak": gbs / peak}
+        d.update(kw)
+        return d
+
+    res = {}
+    n2, Bi = 4096, 16
+    x2 = torch.randn((Bi, n2, n2), dtype=torch.float32, device=dev).permute(2, 1, 0)      # column-major (n, n, B)
+    wl = wb.wavelet(wb.WT.cdf97, wb.WT.Lifting)
+    res["dwt2_cdf97_lifting_4096x4096_f32_L8"] = entry(
+        n2 * n2 * Bi, 4, timed_pair(lambda: wb.dwtc(x2, wl, 8), lambda y: wb.idwtc(y, wl, 8)), images=Bi)
+    wf = wb.wavelet(wb.WT.db4)
+    res["dwt2_db4_filter_4096x4096_f32_L8"] = entry(
+        n2 * n2 * Bi, 4, timed_pair(lambda: wb.dwtc(x2, wf, 8), lambda y: wb.idwtc(y, wf, 8)), images=Bi)
+    del x2
+    x3 = torch.randn((512, 512, 512), dtype=torch.float32, device=dev).permute(2, 1, 0)
+    w6 = wb.wavelet(wb.WT.db6)
+    res["dwt3_db6_512cubed_f32_L3"] = entry(512 ** 3, 4, timed_pair(lambda: wb.dwt(x3, w6, 3), lambda y: wb.idwt(y, w6, 3)))
+    del x3
+    xp = torch.randn((1024, 1 << 16), dtype=torch.float32, device=dev).t()
+    w8 = wb.wavelet(wb.WT.sym8)
+    res["wpt_sym8_fulltree_65536_f32"] = entry((1 << 16) * 1024, 4, timed_pair(lambda: wb.wpt(xp, w8), lambda y: wb.iwpt(y, w8)),
+                                               signals=1024, note="16 levels x 16 taps: FP32-pipe bound, not HBM bound")
     return res
 
 
