@@ -379,8 +379,15 @@ struct Fused1dCfg {
 
 // defaults from the r01 sweep (tools/tune_fused1d.py, profiles/r01_tune_*.log): fewer fused levels (smaller halo) and a
 // larger whole-line tail win once the tails load with TMA
-template <typename T> static int tail_max() { return sizeof(T) == 4 ? env_int("WB200_TAILMAX_F32", 32768) : env_int("WB200_TAILMAX_F64", 16384); }
-template <typename T> static int tile_max() { return sizeof(T) == 4 ? env_int("WB200_TILE_F32", 8192) : env_int("WB200_TILE_F64", 4096); }
+// (Float32 inverse prefers a longer tile / shorter tail than the forward pass: its per-tile halo is tiny, r01 sweep.)
+template <typename T> static int tail_max(bool fw) {
+    if (sizeof(T) == 4) return fw ? env_int("WB200_TAILMAX_F32", 32768) : env_int("WB200_TAILMAX_F32_INV", env_int("WB200_TAILMAX_F32", 16384));
+    return env_int("WB200_TAILMAX_F64", 16384);
+}
+template <typename T> static int tile_max(bool fw) {
+    if (sizeof(T) == 4) return fw ? env_int("WB200_TILE_F32", 8192) : env_int("WB200_TILE_F32_INV", env_int("WB200_TILE_F32", 16384));
+    return env_int("WB200_TILE_F64", 4096);
+}
 
 template <int F, int PA> static int ana_halo(int K, int (&H)[MAXK + 1]) {
     using G = FGeom<F, PA>;
@@ -393,16 +400,16 @@ template <int F, int PA> static int ana_halo(int K, int (&H)[MAXK + 1]) {
 }
 
 template <typename T, int F>
-static Fused1dCfg plan_split(int64_t n, int L) {
+static Fused1dCfg plan_split(int64_t n, int L, bool fw) {
     Fused1dCfg c;
-    const int tmax = tail_max<T>();
+    const int tmax = tail_max<T>(fw);
     const int kcap = env_int("WB200_KMAX", MAXK);
     const int halo_div = env_int("WB200_HALO_DIV", 4);        // accept at most tile/halo_div halo samples per tile
     int64_t cur = n;
     int lv = 0;
     while (cur > tmax && lv < L) {
         if (c.nstages == 8) return c;
-        int64_t tile = tile_max<T>();
+        int64_t tile = tile_max<T>(fw);
         const int64_t p2 = pow2_factor(cur);
         while (tile > p2) tile >>= 1;                          // the tile must divide the line
         while (tile > cur / 2) tile >>= 1;                     // at least two tiles per line (a wrap piece never overlaps its tile)
@@ -502,7 +509,7 @@ static size_t scratch_elems(const Fused1dCfg &cfg, int64_t n, int64_t B, size_t 
 template <typename T, int F, bool STRICT>
 static int32_t run_fused_1d(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t B, int L, bool fw,
                             void *workspace, size_t ws_bytes, cudaStream_t st) {
-    const Fused1dCfg cfg = plan_split<T, F>(n, L);
+    const Fused1dCfg cfg = plan_split<T, F>(n, L, fw);
     if (!cfg.ok) return -1;
     if (cfg.nstages > 0 && (B > 65535 || !syn_plans_ok<T, F>(cfg, n))) return -1;
     Taps<T, F> taps;
@@ -638,9 +645,12 @@ template <typename T> static size_t fused_ws_T(int64_t n, int64_t B, int L) {
         const size_t b = scratch_elems<T>(c, n, B, off) * sizeof(T);
         need = b > need ? b : need;
     };
-    one(plan_split<T, 2>(n, L)); one(plan_split<T, 4>(n, L)); one(plan_split<T, 6>(n, L)); one(plan_split<T, 8>(n, L));
-    one(plan_split<T, 10>(n, L)); one(plan_split<T, 12>(n, L)); one(plan_split<T, 14>(n, L)); one(plan_split<T, 16>(n, L));
-    one(plan_split<T, 18>(n, L)); one(plan_split<T, 20>(n, L));
+    for (int d = 0; d < 2; ++d) {
+        const bool fw = d != 0;
+        one(plan_split<T, 2>(n, L, fw)); one(plan_split<T, 4>(n, L, fw)); one(plan_split<T, 6>(n, L, fw)); one(plan_split<T, 8>(n, L, fw));
+        one(plan_split<T, 10>(n, L, fw)); one(plan_split<T, 12>(n, L, fw)); one(plan_split<T, 14>(n, L, fw)); one(plan_split<T, 16>(n, L, fw));
+        one(plan_split<T, 18>(n, L, fw)); one(plan_split<T, 20>(n, L, fw));
+    }
     return need;
 }
 

@@ -624,7 +624,9 @@ static int32_t launch_level(const T *a, int64_t lda, int64_t bsa, const T *xd, i
         if constexpr (FW) {
             TensorMap tm;
             if (make_tensor_map<T>(tm, a, n, n, B, lda, bsa, C3::PI, C3::RJ)) {
-                auto kern = k_lift2d_fwd_tma<T, S, STRICT, C3>;
+                constexpr bool CAN5 = (sizeof(T) == 4) && !STRICT;
+                const bool occ5 = CAN5 && env_int2("WB200_LIFT2D_OCC5", 0);
+                auto kern = occ5 ? k_lift2d_fwd_tma<T, S, STRICT, C3, CAN5> : k_lift2d_fwd_tma<T, S, STRICT, C3, false>;
                 if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3::SMEM_F) == cudaSuccess) {
                     {
                         LaunchScope scope("fused_lift2d_fwd", st);
@@ -639,7 +641,9 @@ static int32_t launch_level(const T *a, int64_t lda, int64_t bsa, const T *xd, i
             const int nh = n / 2;
             if (make_tensor_map<T>(tml, a, nh, nh, B, lda, bsa, C3::PC, C3::JQ) &&
                 make_tensor_map<T>(tmx, xd, n, n, B, ldx, bsx, C3::PC, C3::JQ)) {
-                auto kern = k_lift2d_inv_tma<T, S, STRICT, C3>;
+                constexpr bool CAN5 = (sizeof(T) == 4) && !STRICT;
+                const bool occ5 = CAN5 && env_int2("WB200_LIFT2D_OCC5", 0);
+                auto kern = occ5 ? k_lift2d_inv_tma<T, S, STRICT, C3, CAN5> : k_lift2d_inv_tma<T, S, STRICT, C3, false>;
                 if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3::SMEM_I) == cudaSuccess) {
                     {
                         LaunchScope scope("fused_lift2d_inv", st);

@@ -143,8 +143,10 @@ template <typename T, class S, int TI_, int TJ_, int SI_, int SJ_> struct Cfg3 {
 // ---------------------------------------------------------------------------------------------------
 // forward level
 // ---------------------------------------------------------------------------------------------------
-template <typename T, class S, bool STRICT, class C>
-__global__ void __launch_bounds__(C::NT)
+// OCC5: size the register budget for five resident CTAs per SM (Float32, non-strict: 40 registers, ~60 B of spill)
+// instead of four -- more tiles in flight to cover the TMA latency.
+template <typename T, class S, bool STRICT, class C, bool OCC5>
+__global__ void __launch_bounds__(C::NT, OCC5 ? 5 : 1)
 k_lift2d_fwd_tma(const __grid_constant__ TensorMap tm_src, const T *__restrict__ src, int64_t ld_s, int64_t bs_s,
                  T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll, T *__restrict__ yd, int64_t ld_y, int64_t bs_y,
                  int n, const __grid_constant__ LiftCoefs<T> lc) {
@@ -260,8 +262,8 @@ k_lift2d_fwd_tma(const __grid_constant__ TensorMap tm_src, const T *__restrict__
 // ---------------------------------------------------------------------------------------------------
 // inverse level
 // ---------------------------------------------------------------------------------------------------
-template <typename T, class S, bool STRICT, class C>
-__global__ void __launch_bounds__(C::NT)
+template <typename T, class S, bool STRICT, class C, bool OCC5>
+__global__ void __launch_bounds__(C::NT, OCC5 ? 5 : 1)
 k_lift2d_inv_tma(const __grid_constant__ TensorMap tm_ll, const __grid_constant__ TensorMap tm_x,
                  const T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll, const T *__restrict__ xd, int64_t ld_x, int64_t bs_x,
                  T *__restrict__ dst, int64_t ld_d, int64_t bs_d, int n, const __grid_constant__ LiftCoefs<T> lc) {
