@@ -617,41 +617,75 @@ template <typename T, class S, bool STRICT, bool FW>
 static int32_t launch_level(const T *a, int64_t lda, int64_t bsa, const T *xd, int64_t ldx, int64_t bsx,
                             T *o1, int64_t ld1, int64_t bs1, T *o2, int64_t ld2, int64_t bs2,
                             int n, int64_t B, const LiftCoefs<T> &lc, cudaStream_t st) {
-    // ---- preferred: tensor-map TMA tiles ----
+    // ---- preferred: tensor-map TMA tiles (persistent double-buffered CTAs when there are enough tiles) ----
     if (env_int2("WB200_LIFT2D_TMA", 1)) {
         using C3 = Cfg3For<S, T>;
-        dim3 grid((unsigned)(n / C3::TI), (unsigned)(n / C3::TJ), (unsigned)B);
-        if constexpr (FW) {
-            TensorMap tm;
-            if (make_tensor_map<T>(tm, a, n, n, B, lda, bsa, C3::PI, C3::RJ)) {
-                constexpr bool CAN5 = (sizeof(T) == 4) && !STRICT;
-                const bool occ5 = CAN5 && env_int2("WB200_LIFT2D_OCC5", 0);
-                auto kern = occ5 ? k_lift2d_fwd_tma<T, S, STRICT, C3, CAN5> : k_lift2d_fwd_tma<T, S, STRICT, C3, false>;
-                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3::SMEM_F) == cudaSuccess) {
-                    {
-                        LaunchScope scope("fused_lift2d_fwd", st);
-                        kern<<<grid, C3::NT, C3::SMEM_F, st>>>(tm, a, lda, bsa, o1, ld1, bs1, o2, ld2, bs2, n, lc);
+        const int nx = n / C3::TI, ny = n / C3::TJ;
+        const int64_t ntiles64 = (int64_t)nx * ny * B;
+        if (ntiles64 <= 0x7fffffffLL) {
+            const int ntiles = (int)ntiles64;
+            int dev = 0, nsm = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+            const size_t one_f = C3::SMEM_F - 128, one_i = C3::SMEM_I - 128;
+            if constexpr (FW) {
+                TensorMap tm;
+                if (make_tensor_map<T>(tm, a, n, n, B, lda, bsa, C3::PI, C3::RJ)) {
+                    const int per_sm = (int)((220 * 1024) / (2 * one_f + 128));
+                    const bool persist = env_int2("WB200_LIFT2D_PERSIST", 0) && per_sm >= 1 && ntiles >= 4 * nsm * per_sm;
+                    const size_t smem = 128 + (persist ? 2 : 1) * one_f;
+                    const int grid = persist ? nsm * per_sm : ntiles;
+                    if (persist) {
+                        auto kern = k_lift2d_fwd_tma_p<T, S, STRICT, C3, 2>;
+                        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+                            {
+                                LaunchScope scope("fused_lift2d_fwd", st);
+                                kern<<<grid, C3::NT, smem, st>>>(tm, a, lda, bsa, o1, ld1, bs1, o2, ld2, bs2, n, nx, ny, ntiles, lc);
+                            }
+                            return check_launch("fused_lift2d_fwd(tma,persistent)") ? WB200_OK : WB200_ECUDA;
+                        }
+                    } else {
+                        auto kern = k_lift2d_fwd_tma<T, S, STRICT, C3>;
+                        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+                            {
+                                LaunchScope scope("fused_lift2d_fwd", st);
+                                kern<<<dim3((unsigned)nx, (unsigned)ny, (unsigned)B), C3::NT, smem, st>>>(tm, a, lda, bsa, o1, ld1, bs1, o2, ld2, bs2, n, lc);
+                            }
+                            return check_launch("fused_lift2d_fwd(tma)") ? WB200_OK : WB200_ECUDA;
+                        }
                     }
-                    return check_launch("fused_lift2d_fwd(tma)") ? WB200_OK : WB200_ECUDA;
+                    (void)cudaGetLastError();
                 }
-                (void)cudaGetLastError();
-            }
-        } else {
-            TensorMap tml, tmx;
-            const int nh = n / 2;
-            if (make_tensor_map<T>(tml, a, nh, nh, B, lda, bsa, C3::PC, C3::JQ) &&
-                make_tensor_map<T>(tmx, xd, n, n, B, ldx, bsx, C3::PC, C3::JQ)) {
-                constexpr bool CAN5 = (sizeof(T) == 4) && !STRICT;
-                const bool occ5 = CAN5 && env_int2("WB200_LIFT2D_OCC5", 0);
-                auto kern = occ5 ? k_lift2d_inv_tma<T, S, STRICT, C3, CAN5> : k_lift2d_inv_tma<T, S, STRICT, C3, false>;
-                if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3::SMEM_I) == cudaSuccess) {
-                    {
-                        LaunchScope scope("fused_lift2d_inv", st);
-                        kern<<<grid, C3::NT, C3::SMEM_I, st>>>(tml, tmx, a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, n, lc);
+            } else {
+                TensorMap tml, tmx;
+                const int nh = n / 2;
+                if (make_tensor_map<T>(tml, a, nh, nh, B, lda, bsa, C3::PC, C3::JQ) &&
+                    make_tensor_map<T>(tmx, xd, n, n, B, ldx, bsx, C3::PC, C3::JQ)) {
+                    const int per_sm = (int)((220 * 1024) / (2 * one_i + 128));
+                    const bool persist = env_int2("WB200_LIFT2D_PERSIST", 0) && per_sm >= 1 && ntiles >= 4 * nsm * per_sm;
+                    const size_t smem = 128 + (persist ? 2 : 1) * one_i;
+                    const int grid = persist ? nsm * per_sm : ntiles;
+                    if (persist) {
+                        auto kern = k_lift2d_inv_tma_p<T, S, STRICT, C3, 2>;
+                        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+                            {
+                                LaunchScope scope("fused_lift2d_inv", st);
+                                kern<<<grid, C3::NT, smem, st>>>(tml, tmx, a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, n, nx, ny, ntiles, lc);
+                            }
+                            return check_launch("fused_lift2d_inv(tma,persistent)") ? WB200_OK : WB200_ECUDA;
+                        }
+                    } else {
+                        auto kern = k_lift2d_inv_tma<T, S, STRICT, C3>;
+                        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess) {
+                            {
+                                LaunchScope scope("fused_lift2d_inv", st);
+                                kern<<<dim3((unsigned)nx, (unsigned)ny, (unsigned)B), C3::NT, smem, st>>>(tml, tmx, a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, n, lc);
+                            }
+                            return check_launch("fused_lift2d_inv(tma)") ? WB200_OK : WB200_ECUDA;
+                        }
                     }
-                    return check_launch("fused_lift2d_inv(tma)") ? WB200_OK : WB200_ECUDA;
+                    (void)cudaGetLastError();
                 }
-                (void)cudaGetLastError();
             }
         }
     }

@@ -133,7 +133,7 @@ template <typename T, class S, int TI_, int TJ_, int SI_, int SJ_> struct Cfg3 {
     static constexpr int MAXT_ = ROW_TASKS_F > COL_TASKS_F ? ROW_TASKS_F : COL_TASKS_F;
     static constexpr int MAXI_ = COL_TASKS_I > ROW_TASKS_I ? COL_TASKS_I : ROW_TASKS_I;
     static constexpr int NT = ((MAXT_ > MAXI_ ? MAXT_ : MAXI_) + 31) / 32 * 32;
-    static constexpr size_t SMEM_F = 128 + (size_t)RJ * PI * sizeof(T);
+    static constexpr size_t SMEM_F = 128 + ((size_t)RJ * PI * sizeof(T) + 127) / 128 * 128;   // per buffer (+128 header once)
     static constexpr int QSZ = (JQ * PC * (int)sizeof(T) + 127) / 128 * 128 / (int)sizeof(T);   // one quadrant array, 128-byte multiple (TMA destination alignment)
     static constexpr size_t SMEM_I = 128 + (size_t)4 * QSZ * sizeof(T);
     static_assert(TIp % SI == 0 && TJp % SJ == 0, "segments must tile the tile");
@@ -143,10 +143,288 @@ template <typename T, class S, int TI_, int TJ_, int SI_, int SJ_> struct Cfg3 {
 // ---------------------------------------------------------------------------------------------------
 // forward level
 // ---------------------------------------------------------------------------------------------------
-// OCC5: size the register budget for five resident CTAs per SM (Float32, non-strict: 40 registers, ~60 B of spill)
-// instead of four -- more tiles in flight to cover the TMA latency.
-template <typename T, class S, bool STRICT, class C, bool OCC5>
-__global__ void __launch_bounds__(C::NT, OCC5 ? 5 : 1)
+// NBUF = 1: one tile per CTA (grid = all tiles).  NBUF = 2: PERSISTENT CTAs walk the tile list with two shared-memory
+// buffers -- the TMA box of tile k+1 is in flight while tile k is transformed (the top stall of the one-shot kernel is
+// the wait for its own tile, profiles/r01_lift2d_f32_tma.md).
+template <typename T, class S, bool STRICT, class C, int NBUF>
+__global__ void __launch_bounds__(C::NT, (NBUF == 1 ? 4 : 2) / (int)(sizeof(T) / 4))   // resident CTAs the register budget is sized for
+k_lift2d_fwd_tma_p(const __grid_constant__ TensorMap tm_src, const T *__restrict__ src, int64_t ld_s, int64_t bs_s,
+                 T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll, T *__restrict__ yd, int64_t ld_y, int64_t bs_y,
+                 int n, int nx, int ny, int ntiles, const __grid_constant__ LiftCoefs<T> lc) {
+    using fp = FP<STRICT>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    constexpr int BUFSZ = (C::RJ * C::PI * (int)sizeof(T) + 127) / 128 * 128 / (int)sizeof(T);
+    T *Sm0 = reinterpret_cast<T *>(smem_raw + 128);
+    const int nh = n >> 1;
+    const int tid = threadIdx.x;
+    auto issue = [&](int tile, int buf) {
+        const int tx = tile % nx, r = tile / nx;
+        mb_expect(bars + buf, (uint32_t)(C::RJ * C::PI * sizeof(T)));
+        tma_box3(Sm0 + buf * BUFSZ, &tm_src, tx * C::TI - C::HLS, (r % ny) * C::TJ - 2 * C::HL, r / ny, bars + buf);
+    };
+    if (tid == 0) {
+        for (int q = 0; q < NBUF; ++q) mb_init(bars + q);
+        if ((int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+    }
+    __syncthreads();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int cur = (NBUF == 2) ? (it & 1) : 0;
+    T *Sm = Sm0 + cur * BUFSZ;
+    const int txi = tile % nx, tr = tile / nx, tyi = tr % ny;
+    const int b = tr / ny;
+    const int i0 = txi * C::TI, j0 = tyi * C::TJ;
+    const int iorg = i0 - C::HLS, jorg = j0 - 2 * C::HL;          // global coordinates of local (0, 0)
+    if (NBUF == 2 && tid == 0 && tile + (int)gridDim.x < ntiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy accesses of that buffer are done (barrier below)
+        issue(tile + gridDim.x, cur ^ 1);
+    }
+    mb_wait(bars + cur, (NBUF == 2) ? ((it >> 1) & 1) : 0);
+    // ---- periodic wrap: border tiles patch the halo cells the tensor map zero-filled ----
+    const bool edge_i = (txi == 0) || (txi == nx - 1);
+    const bool edge_j = (tyi == 0) || (tyi == ny - 1);
+    if (edge_i || edge_j) {
+        const T *sb = src + (int64_t)b * bs_s;
+        constexpr int WI = C::HLS + C::TI + 2 * C::HR;
+        for (int idx = tid; idx < C::RJ * WI; idx += C::NT) {
+            const int r = idx / WI, il = idx - r * WI;
+            const int gi = iorg + il, gj = jorg + r;
+            if (gi < 0 || gi >= n || gj < 0 || gj >= n)
+                Sm[r * C::PI + il] = sb[(int64_t)wrapi(gj, n) * ld_s + wrapi(gi, n)];
+        }
+        __syncthreads();
+    }
+    // ---- dim-2 pass: one thread per (dim-1 sample, segment of dim-2 pairs) ----
+    {
+        T s[C::NPJ], d[C::NPJ];
+        const bool act = tid < C::ROW_TASKS_F;
+        constexpr int WI = 2 * C::HL + C::TI + 2 * C::HR;
+        int il = 0, q = 0;
+        if (act) {
+            il = (C::HLS - 2 * C::HL) + tid % WI;
+            q = tid / WI;
+#pragma unroll
+            for (int pp = 0; pp < C::NPJ; ++pp) {
+                s[pp] = Sm[(2 * (q * C::SJ + pp)) * C::PI + il];
+                d[pp] = Sm[(2 * (q * C::SJ + pp) + 1) * C::PI + il];
+            }
+        }
+        __syncthreads();
+        if (act) {
+            const int jp0 = (j0 >> 1) - C::HL + q * C::SJ;
+            lift_regs<T, S, STRICT, C::NPJ>(s, d, lc, wrapi(jp0, nh), nh, STRICT && edge_j);
+#pragma unroll
+            for (int pp = C::HL; pp < C::HL + C::SJ; ++pp) {
+                Sm[(2 * (q * C::SJ + pp)) * C::PI + il] = fp::mul(s[pp], lc.n1);
+                Sm[(2 * (q * C::SJ + pp) + 1) * C::PI + il] = fp::mul(d[pp], lc.n2);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- dim-1 pass: one thread per (owned row, segment); 16-byte shared-memory accesses ----
+    {
+        T w[C::WINF];
+        T s[C::NPI], d[C::NPI];
+        const bool act = tid < C::COL_TASKS_F;
+        constexpr int OFF = C::HLS - 2 * C::HL;           // samples between the vector-aligned window start and pair 0
+        int r = 0, q = 0;
+        if (act) {
+            r = 2 * C::HL + tid % C::TJ;
+            q = tid / C::TJ;
+            lds16<T, C::WINF>(w, Sm + r * C::PI + 2 * q * C::SI);
+#pragma unroll
+            for (int pp = 0; pp < C::NPI; ++pp) { s[pp] = w[OFF + 2 * pp]; d[pp] = w[OFF + 2 * pp + 1]; }
+        }
+        __syncthreads();
+        if (act) {
+            lift_regs<T, S, STRICT, C::NPI>(s, d, lc, wrapi((i0 >> 1) - C::HL + q * C::SI, nh), nh, STRICT && edge_i);
+            T o[2 * C::SI];
+#pragma unroll
+            for (int pp = 0; pp < C::SI; ++pp) {
+                o[2 * pp] = fp::mul(s[C::HL + pp], lc.n1);
+                o[2 * pp + 1] = fp::mul(d[C::HL + pp], lc.n2);
+            }
+            sts16<T, 2 * C::SI>(Sm + r * C::PI + C::HLS + 2 * q * C::SI, o);   // HLS is a vector multiple: aligned
+        }
+        __syncthreads();
+    }
+    // ---- stores: a thread reads one 16-byte piece of an owned row and writes its s-part and d-part ----
+    {
+        T *llb = ll + (int64_t)b * bs_ll;
+        T *yb = yd + (int64_t)b * bs_y;
+        constexpr int VPR = C::TI / C::V;                 // vectors per owned row
+        for (int idx = tid; idx < C::TJ * VPR; idx += C::NT) {
+            const int t = idx % VPR, rr = idx / VPR;
+            const int j = j0 + rr, jq = j >> 1, pj = j & 1;
+            T w[C::V];
+            lds16<T, C::V>(w, Sm + (2 * C::HL + rr) * C::PI + C::HLS + t * C::V);
+            const int ip = (i0 >> 1) + t * (C::V / 2);
+            T *ps = (pj == 0) ? (llb + (int64_t)jq * ld_ll + ip) : (yb + (int64_t)(nh + jq) * ld_y + ip);
+            T *pd = yb + (int64_t)(pj * nh + jq) * ld_y + nh + ip;
+            if constexpr (sizeof(T) == 4) {
+                *reinterpret_cast<float2 *>(ps) = make_float2(w[0], w[2]);
+                *reinterpret_cast<float2 *>(pd) = make_float2(w[1], w[3]);
+            } else {
+                ps[0] = w[0];
+                pd[0] = w[1];
+            }
+        }
+    }
+    __syncthreads();   // every thread is done with this buffer before it is refilled
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// inverse level
+// ---------------------------------------------------------------------------------------------------
+template <typename T, class S, bool STRICT, class C, int NBUF>
+__global__ void __launch_bounds__(C::NT, (NBUF == 1 ? 4 : 2) / (int)(sizeof(T) / 4))
+k_lift2d_inv_tma_p(const __grid_constant__ TensorMap tm_ll, const __grid_constant__ TensorMap tm_x,
+                 const T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll, const T *__restrict__ xd, int64_t ld_x, int64_t bs_x,
+                 T *__restrict__ dst, int64_t ld_d, int64_t bs_d, int n, int nx, int ny, int ntiles,
+                 const __grid_constant__ LiftCoefs<T> lc) {
+    using fp = FP<STRICT>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    T *Sm0 = reinterpret_cast<T *>(smem_raw + 128);
+    constexpr int QSZ = C::QSZ;                           // one quadrant array; order [pi][pj]
+    const int nh = n >> 1;
+    const int tid = threadIdx.x;
+    auto issue = [&](int tile, int buf) {
+        const int tx = tile % nx, r = tile / nx;
+        const int c = tx * C::TIp - C::CO, q = (r % ny) * C::TJp - C::HL, bb = r / ny;
+        T *B0 = Sm0 + buf * 4 * QSZ;
+        mb_expect(bars + buf, (uint32_t)(4 * C::JQ * C::PC * sizeof(T)));
+        tma_box3(B0 + 0 * QSZ, &tm_ll, c, q, bb, bars + buf);                 // (pi, pj) = (0, 0): LL
+        tma_box3(B0 + 1 * QSZ, &tm_x, c, nh + q, bb, bars + buf);             // (0, 1)
+        tma_box3(B0 + 2 * QSZ, &tm_x, nh + c, q, bb, bars + buf);             // (1, 0)
+        tma_box3(B0 + 3 * QSZ, &tm_x, nh + c, nh + q, bb, bars + buf);        // (1, 1)
+    };
+    if (tid == 0) {
+        for (int q = 0; q < NBUF; ++q) mb_init(bars + q);
+        if ((int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+    }
+    __syncthreads();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int cur = (NBUF == 2) ? (it & 1) : 0;
+    T *Sm = Sm0 + cur * 4 * QSZ;
+    const int txi = tile % nx, tr = tile / nx, tyi = tr % ny;
+    const int b = tr / ny;
+    const int ip0 = txi * C::TIp, jq0 = tyi * C::TJp;
+    const int corg = ip0 - C::CO, qorg = jq0 - C::HL;     // quadrant coordinates of local (0, 0)
+    if (NBUF == 2 && tid == 0 && tile + (int)gridDim.x < ntiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(tile + gridDim.x, cur ^ 1);
+    }
+    mb_wait(bars + cur, (NBUF == 2) ? ((it >> 1) & 1) : 0);
+    const bool edge_i = (txi == 0) || (txi == nx - 1);
+    const bool edge_j = (tyi == 0) || (tyi == ny - 1);
+    if (edge_i || edge_j) {   // quadrant-relative wrap of the halo cells
+        const T *llb = ll + (int64_t)b * bs_ll;
+        const T *xb = xd + (int64_t)b * bs_x;
+        for (int idx = tid; idx < 4 * C::JQ * C::IW; idx += C::NT) {
+            const int c = idx % C::IW;
+            const int rest = idx / C::IW;
+            const int ql = rest % C::JQ, quad = rest / C::JQ;
+            const int gc = corg + c, gq = qorg + ql;
+            if (gc < 0 || gc >= nh || gq < 0 || gq >= nh) {
+                const int wc = wrapi(gc, nh), wq = wrapi(gq, nh);
+                const int pi = quad >> 1, pj = quad & 1;
+                Sm[quad * QSZ + ql * C::PC + c] = (quad == 0) ? llb[(int64_t)wq * ld_ll + wc]
+                                                              : xb[(int64_t)(pj * nh + wq) * ld_x + pi * nh + wc];
+            }
+        }
+        __syncthreads();
+    }
+    // ---- dim-1 pass first (inverse order): s_i = quadrant (0, pj), d_i = quadrant (1, pj), on every staged dim-2 pair
+    {
+        T ws[C::WINI], wd[C::WINI];
+        T s[C::NPI], d[C::NPI];
+        const bool act = tid < C::COL_TASKS_I;
+        constexpr int OFF = C::CO - C::HL;
+        T *As = Sm, *Ad = Sm;
+        int q = 0;
+        if (act) {
+            const int ql = tid % C::JQ;
+            const int rest = tid / C::JQ;
+            const int pj = rest & 1;
+            q = rest >> 1;
+            As = Sm + (0 * 2 + pj) * QSZ + ql * C::PC + q * C::SI;
+            Ad = Sm + (1 * 2 + pj) * QSZ + ql * C::PC + q * C::SI;
+            lds16<T, C::WINI>(ws, As);
+            lds16<T, C::WINI>(wd, Ad);
+#pragma unroll
+            for (int pp = 0; pp < C::NPI; ++pp) { s[pp] = fp::mul(ws[OFF + pp], lc.n1); d[pp] = fp::mul(wd[OFF + pp], lc.n2); }
+        }
+        __syncthreads();
+        if (act) {
+            lift_regs<T, S, STRICT, C::NPI>(s, d, lc, wrapi(ip0 - C::HL + q * C::SI, nh), nh, STRICT && edge_i);
+            T os[C::SI], od[C::SI];
+#pragma unroll
+            for (int pp = 0; pp < C::SI; ++pp) { os[pp] = s[C::HL + pp]; od[pp] = d[C::HL + pp]; }
+            sts16<T, C::SI>(As + C::CO, os);
+            sts16<T, C::SI>(Ad + C::CO, od);
+        }
+        __syncthreads();
+    }
+    // ---- dim-2 pass on the owned dim-1 pairs: s_j = quadrant (pi, 0), d_j = quadrant (pi, 1) ----
+    {
+        T s[C::NPJ], d[C::NPJ];
+        const bool act = tid < C::ROW_TASKS_I;
+        T *A0 = Sm, *A1 = Sm;
+        int q = 0;
+        if (act) {
+            const int c = C::CO + tid % C::TIp;
+            const int rest = tid / C::TIp;
+            const int pi = rest & 1;
+            q = rest >> 1;
+            A0 = Sm + (pi * 2 + 0) * QSZ + (q * C::SJ) * C::PC + c;
+            A1 = Sm + (pi * 2 + 1) * QSZ + (q * C::SJ) * C::PC + c;
+#pragma unroll
+            for (int pp = 0; pp < C::NPJ; ++pp) { s[pp] = fp::mul(A0[pp * C::PC], lc.n1); d[pp] = fp::mul(A1[pp * C::PC], lc.n2); }
+        }
+        __syncthreads();
+        if (act) {
+            lift_regs<T, S, STRICT, C::NPJ>(s, d, lc, wrapi(jq0 - C::HL + q * C::SJ, nh), nh, STRICT && edge_j);
+#pragma unroll
+            for (int pp = C::HL; pp < C::HL + C::SJ; ++pp) { A0[pp * C::PC] = s[pp]; A1[pp * C::PC] = d[pp]; }
+        }
+        __syncthreads();
+    }
+    // ---- merged store: out[2ip + pi, 2jq + pj] ----
+    {
+        T *db = dst + (int64_t)b * bs_d;
+        constexpr int VPR = C::TIp / C::V;                // 16-byte pieces per owned quadrant row
+        for (int idx = tid; idx < 2 * C::TJp * VPR; idx += C::NT) {
+            const int t = idx % VPR;
+            const int rest = idx / VPR;
+            const int pj = rest & 1, qq = rest >> 1;       // owned dim-2 pair qq
+            const int ql = C::HL + qq;
+            T ws[C::V], wd[C::V];
+            lds16<T, C::V>(ws, Sm + (0 * 2 + pj) * QSZ + ql * C::PC + C::CO + t * C::V);
+            lds16<T, C::V>(wd, Sm + (1 * 2 + pj) * QSZ + ql * C::PC + C::CO + t * C::V);
+            T *p = db + (int64_t)(2 * (jq0 + qq) + pj) * ld_d + 2 * (ip0 + t * C::V);
+            if constexpr (sizeof(T) == 4) {
+                *reinterpret_cast<float4 *>(p) = make_float4(ws[0], wd[0], ws[1], wd[1]);
+                *reinterpret_cast<float4 *>(p + 4) = make_float4(ws[2], wd[2], ws[3], wd[3]);
+            } else {
+                *reinterpret_cast<double2 *>(p) = make_double2(ws[0], wd[0]);
+                *reinterpret_cast<double2 *>(p + 2) = make_double2(ws[1], wd[1]);
+            }
+        }
+    }
+    __syncthreads();   // every thread is done with this buffer before it is refilled
+    }
+}
+
+// ===================================================================================================
+// one-shot variants (one tile per CTA): used when there are too few tiles to keep persistent CTAs busy
+// ===================================================================================================
+// one tile per CTA
+template <typename T, class S, bool STRICT, class C>
+__global__ void __launch_bounds__(C::NT)
 k_lift2d_fwd_tma(const __grid_constant__ TensorMap tm_src, const T *__restrict__ src, int64_t ld_s, int64_t bs_s,
                  T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll, T *__restrict__ yd, int64_t ld_y, int64_t bs_y,
                  int n, const __grid_constant__ LiftCoefs<T> lc) {
@@ -262,8 +540,8 @@ k_lift2d_fwd_tma(const __grid_constant__ TensorMap tm_src, const T *__restrict__
 // ---------------------------------------------------------------------------------------------------
 // inverse level
 // ---------------------------------------------------------------------------------------------------
-template <typename T, class S, bool STRICT, class C, bool OCC5>
-__global__ void __launch_bounds__(C::NT, OCC5 ? 5 : 1)
+template <typename T, class S, bool STRICT, class C>
+__global__ void __launch_bounds__(C::NT)
 k_lift2d_inv_tma(const __grid_constant__ TensorMap tm_ll, const __grid_constant__ TensorMap tm_x,
                  const T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll, const T *__restrict__ xd, int64_t ld_x, int64_t bs_x,
                  T *__restrict__ dst, int64_t ld_d, int64_t bs_d, int n, const __grid_constant__ LiftCoefs<T> lc) {
