@@ -111,6 +111,17 @@ int32_t wb200_wpt_lifting(void *y, const void *x, int64_t n, int64_t batch,
                           const uint8_t *tree, int64_t ntree, int32_t fw, int32_t dtype,
                           void *workspace, size_t workspace_bytes, void *stream, uint32_t flags);
 
+/* ---- maximal-overlap (undecimated) DWT: replaces modwt(x, wt, L) / imodwt(xw, wt)
+ * (src/Transforms/transforms_maximal_overlap.jl:44-62, 98-108; SURVEY 8f "next" row 1).  x: n samples x `batch`
+ * signals; y / xw: n x (L+1) column-major per signal (W_1 .. W_L, V_L), signals back to back.  Float32/Float64.
+ * 1 <= L <= floor(log2(n)) (WB200_ELEVEL otherwise: "Too many transform levels (length(x) < 2^L)" / "L must be >= 1").
+ * Scratch: n * batch elements (workspace = NULL: stream-ordered pool). */
+int32_t wb200_modwt(void *y, const void *x, int64_t n, int64_t batch, const double *qmf, int32_t flen, int32_t L,
+                    int32_t dtype, void *workspace, size_t workspace_bytes, void *stream, uint32_t flags);
+int32_t wb200_imodwt(void *x, const void *xw, int64_t n, int64_t batch, const double *qmf, int32_t flen, int32_t ncols,
+                     int32_t dtype, void *workspace, size_t workspace_bytes, void *stream, uint32_t flags);
+int32_t wb200_maxmodwttransformlevels(int64_t n);                             /* non_dyadic.jl:24-25 */
+
 /* ---- host-buffer forms (end-to-end path): x_host / y_host are HOST pointers (pinned memory gives full
  * PCIe bandwidth).  The batch is cut into chunks that are copied in, transformed and copied out on
  * alternating streams so the three stages overlap; the call returns after the last chunk has landed

@@ -104,6 +104,24 @@ function _wpt!(y::CuVector{T}, scheme::GLS, tree::BitVector, fw::Bool) where T
     check(rc); y
 end
 
+# ---- maximal-overlap DWT: modwt(x, wt, L) / imodwt(xw, wt)  (transforms_maximal_overlap.jl:44-62, 98-108) ----------
+function Wavelets.modwt(x::CuVector{T}, wt::OrthoFilter, L::Integer=maxmodwttransformlevels(x)) where {T<:Union{Float32,Float64}}
+    L <= maxmodwttransformlevels(x) || throw(ArgumentError("Too many transform levels (length(x) < 2^L)"))
+    L >= 1 || throw(ArgumentError("L must be >= 1"))
+    qmf = Vector{Float64}(wt.qmf); y = CuArray{T}(undef, length(x), L + 1)
+    rc = ccall((:wb200_modwt, LIB), Int32,
+               (CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Int64, Ptr{Float64}, Int32, Int32, Int32, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}, UInt32),
+               pointer(y), pointer(x), length(x), 1, qmf, length(qmf), L, dtype_code(T), CU_NULL, 0, CUDA.stream().handle, flags())
+    check(rc); y
+end
+function Wavelets.imodwt(xw::CuMatrix{T}, wt::OrthoFilter) where {T<:Union{Float32,Float64}}
+    qmf = Vector{Float64}(wt.qmf); x = CuArray{T}(undef, size(xw, 1))
+    rc = ccall((:wb200_imodwt, LIB), Int32,
+               (CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Int64, Ptr{Float64}, Int32, Int32, Int32, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}, UInt32),
+               pointer(x), pointer(xw), size(xw, 1), 1, qmf, length(qmf), size(xw, 2), dtype_code(T), CU_NULL, 0, CUDA.stream().handle, flags())
+    check(rc); x
+end
+
 # ---- column-wise batch forms (the last dimension indexes independent signals / images) ---------------------------
 export dwtc, idwtc
 dwtc(x::CuArray, wt::OrthoFilter, L::Integer=minimum(maxtransformlevels.(size(x)[1:end-1]))) =

@@ -186,3 +186,30 @@ def maxtransformlevels(n: int) -> int:
 def isvalidtree(n: int, tree) -> bool:
     t = np.ascontiguousarray(tree, dtype=np.uint8)
     return bool(lib().orc_isvalidtree(C.c_int64(int(n)), t.ctypes.data_as(C.c_void_p), C.c_int64(len(t))))
+
+
+def modwt(x, qmf, L=None):
+    """Reference `modwt(x, wt, L)`: returns the n x (L+1) matrix [W_1 .. W_L V_L]."""
+    x = np.ascontiguousarray(x)
+    sfx, ct = _sfx(x.dtype)
+    n = x.shape[0]
+    if L is None:
+        L = int(np.floor(np.log2(n)))
+    y = np.empty((n, L + 1), dtype=x.dtype, order="F")
+    q = np.ascontiguousarray(qmf, dtype=np.float64)
+    rc = getattr(lib(), "orc_modwt" + sfx)(y.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), C.c_int64(n),
+                                            q.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(len(q)), C.c_int(int(L)))
+    _check(rc)
+    return y
+
+
+def imodwt(xw, qmf):
+    xw = np.asfortranarray(xw)
+    sfx, ct = _sfx(xw.dtype)
+    n, ncols = xw.shape
+    x = np.empty(n, dtype=xw.dtype)
+    q = np.ascontiguousarray(qmf, dtype=np.float64)
+    rc = getattr(lib(), "orc_imodwt" + sfx)(x.ctypes.data_as(C.c_void_p), xw.ctypes.data_as(C.c_void_p), C.c_int64(n),
+                                             C.c_int(ncols), q.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(len(q)))
+    _check(rc)
+    return x

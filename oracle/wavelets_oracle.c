@@ -17,6 +17,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
  * arm may load this library.  The product (libwavelets_b200.so) never does.
  */
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>

@@ -568,3 +568,69 @@ def test_fastpass_wpt_full_tree(dev, mode, dtype, n, B, wname):
         for b in range(B):
             check(np.ascontiguousarray(yn[:, b]), orc.wpt_filter(x[:, b].copy(), wf.qmf, t), mode, L, 4.0)
             check(np.ascontiguousarray(xn[:, b]), orc.wpt_filter(yn[:, b].copy(), wf.qmf, t, fw=False), mode, L, 4.0)
+
+
+# ------------------------------------------------------------------------------------------------------
+# MODWT (transforms_maximal_overlap.jl, test/transforms.jl:325-344)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("wname,n,L", [("db4", 128, None), ("db4", 129, None), ("db4", 129, 4), ("haar", 37, 5),
+                                        ("sym8", 20, 4), ("db2", 5000, 7), ("coif4", 1000, 9)])
+def test_modwt_vs_oracle(dev, mode, dtype, wname, n, L):
+    wt = wavelet(getattr(WT, wname))
+    q = np.asarray(wt.qmf)
+    x = np.cumsum(rng(n).standard_normal(n)).astype(dtype)
+    ref = orc.modwt(x, q, L)
+    W = wb.modwt(to_gpu(x, dev), wt) if L is None else wb.modwt(to_gpu(x, dev), wt, L)
+    assert tuple(W.shape) == ref.shape
+    scale = float(np.max(np.abs(x)))
+    if mode == "strict":
+        assert np.array_equal(to_np(W), ref)
+    else:
+        tol = (2e-6 if dtype == np.float32 else 1e-13) * max(1.0, scale) * ref.shape[1]
+        assert np.max(np.abs(to_np(W).astype(np.float64) - ref)) <= tol
+    back = wb.imodwt(W, wt)
+    refb = orc.imodwt(ref, q)
+    if mode == "strict":
+        assert np.array_equal(to_np(back), refb)
+    tol = (5e-6 if dtype == np.float32 else 1e-11) * max(1.0, scale)
+    assert np.max(np.abs(to_np(back).astype(np.float64) - x)) <= tol
+
+
+def test_modwt_batch_partial_levels_and_errors(dev):
+    wt = wavelet(WT.db4)
+    q = np.asarray(wt.qmf)
+    n, B = 129, 5
+    x = np.cumsum(rng(9).standard_normal((n, B)), axis=0)
+    W = wb.modwt(to_gpu(x, dev), wt)
+    assert tuple(W.shape) == (n, wb.maxmodwttransformlevels(n) + 1, B)
+    wb.set_strict_fp(True)
+    try:
+        Ws = to_np(wb.modwt(to_gpu(x, dev), wt))
+        for b in range(B):
+            assert np.array_equal(Ws[:, :, b], orc.modwt(x[:, b].copy(), q))
+    finally:
+        wb.set_strict_fp(False)
+    back = to_np(wb.imodwt(W, wt))
+    assert np.max(np.abs(back - x)) < 1e-10
+    Wl = wb.modwt(to_gpu(x, dev), wt, 4)
+    assert np.allclose(to_np(W)[:, :3], to_np(Wl)[:, :3], rtol=0, atol=1e-12)
+    with pytest.raises(wb.ArgumentError, match="Too many transform levels"):
+        wb.modwt(to_gpu(x, dev), wt, 8)
+    with pytest.raises(wb.ArgumentError, match="L must be >= 1"):
+        wb.modwt(to_gpu(x, dev), wt, 0)
+    with pytest.raises(TypeError):
+        wb.modwt(to_gpu(x, dev), wavelet(WT.cdf97, WT.Lifting))
+    # one-column xw: imodwt returns V_0 itself
+    v = to_gpu(x[:, :1].reshape(n, 1), dev)
+    assert np.array_equal(to_np(wb.imodwt(v, wt)), x[:, 0])
+
+
+def test_modwt_large_batch_energy(dev):
+    """size-independent property at scale: the undecimated orthogonal bank preserves energy, and imodwt inverts it"""
+    wt = wavelet(WT.db4)
+    x = torch.randn(1 << 16, 64, device=dev, dtype=torch.float64).t().contiguous().t()
+    W = wb.modwt(x, wt, 10)
+    e0, e1 = float((x ** 2).sum()), float((W ** 2).sum())
+    assert abs(e1 - e0) <= 1e-10 * e0
+    assert float((wb.imodwt(W, wt) - x).abs().max()) < 1e-10

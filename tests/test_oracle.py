@@ -175,3 +175,49 @@ def test_batch_driver_matches_loop():
     yb = orc.dwt_filter_batch(x, 1, wt.qmf, 6, nthreads=2)
     for b in range(5):
         assert np.array_equal(yb[:, b], orc.dwt_filter(x[:, b].copy(), wt.qmf, 6))
+
+
+# ------------------------------------------------------------------------------------------------------
+# MODWT: the reference holds no golden vector for it, only relations (test/transforms.jl:325-344).
+# Those, plus a pin onto the golden-checked decimated transform: the level-1 MODWT bands, decimated and scaled by
+# sqrt(2), are the level-1 DWT bands.
+# ------------------------------------------------------------------------------------------------------
+def test_modwt_reference_relations():
+    q = np.asarray(wavelet(WT.db4).qmf)
+    x = rng(1).standard_normal(128)
+    W = orc.modwt(x, q)
+    assert W.shape == (128, 8)
+    assert np.allclose(orc.imodwt(W, q), x, rtol=0, atol=1e-12)
+    x = np.cumsum(rng(2).standard_normal(129))
+    W = orc.modwt(x, q)
+    assert W.shape == (129, int(np.floor(np.log2(129))) + 1)
+    assert np.allclose(orc.imodwt(W, q), x, rtol=0, atol=1e-11)
+    Wl = orc.modwt(x, q, 4)
+    assert np.array_equal(W[:, :3], Wl[:, :3])
+    # energy is preserved by the undecimated orthogonal filter bank
+    assert abs(np.sum(W ** 2) - np.sum(x ** 2)) <= 1e-9 * np.sum(x ** 2)
+    with pytest.raises(orc.OracleError):
+        orc.modwt(x, q, 8)
+    with pytest.raises(orc.OracleError):
+        orc.modwt(x, q, 0)
+
+
+@pytest.mark.parametrize("wname", ["haar", "db2", "db4", "sym6", "coif2", "beyl"])
+def test_modwt_level1_is_undecimated_dwt(wname):
+    q = np.asarray(wavelet(getattr(WT, wname)).qmf)
+    F, n = len(q), 96
+    x = rng(3).standard_normal(n)
+    W = orc.modwt(x, q, 1)
+    y = orc.dwt_filter(x, q, 1)
+    k = np.arange(n // 2)
+    assert np.allclose(np.sqrt(2) * W[(2 * k + F - 1) % n, 1], y[: n // 2], rtol=0, atol=1e-13)
+    assert np.allclose(np.sqrt(2) * W[(2 * k + 1) % n, 0], y[n // 2:], rtol=0, atol=1e-13)
+
+
+def test_modwt_float32():
+    q = np.asarray(wavelet(WT.db2).qmf)
+    x = rng(4).standard_normal(100).astype(np.float32)
+    W = orc.modwt(x, q, 3)
+    assert W.dtype == np.float32
+    assert np.allclose(orc.imodwt(W, q), x, rtol=0, atol=2e-6)
+    assert np.allclose(W, orc.modwt(x.astype(np.float64), q, 3), rtol=0, atol=2e-6)

@@ -13,10 +13,10 @@ from . import wt as WT
 from . import util as Util
 from .wt import wavelet
 from .util import maxtransformlevels, maketree, isvalidtree, detailindex, detailrange, detailn
-from .transforms import (dwt, idwt, dwt_, idwt_, wpt, iwpt, wpt_, iwpt_, dwtc, idwtc, dwt_oop_, idwt_oop_,
+from .transforms import (modwt, imodwt, maxmodwttransformlevels, dwt, idwt, dwt_, idwt_, wpt, iwpt, wpt_, iwpt_, dwtc, idwtc, dwt_oop_, idwt_oop_,
                          ArgumentError, DimensionMismatch, set_strict_fp, colmajor)
 
-__all__ = ["WT", "Util", "wavelet", "maxtransformlevels", "maketree", "isvalidtree", "detailindex",
+__all__ = ["modwt", "imodwt", "maxmodwttransformlevels", "WT", "Util", "wavelet", "maxtransformlevels", "maketree", "isvalidtree", "detailindex",
            "detailrange", "detailn", "dwt", "idwt", "dwt_", "idwt_", "wpt", "iwpt", "wpt_", "iwpt_",
            "dwtc", "idwtc", "dwt_oop_", "idwt_oop_", "ArgumentError", "DimensionMismatch",
            "set_strict_fp", "colmajor"]

@@ -28,6 +28,7 @@ SYMBOLS = [
     "wb200_maxtransformlevels", "wb200_isvalidtree", "wb200_status_string",
     "wb200_last_error_string", "wb200_version", "wb200_launch_count",
     "wb200_profile_enable", "wb200_profile_collect",
+    "wb200_modwt", "wb200_imodwt", "wb200_maxmodwttransformlevels",
 ]
 
 
@@ -56,6 +57,12 @@ def lib() -> C.CDLL:
     L.wb200_wpt_lifting.argtypes = [vp, vp, i64, i64, pst, i32, dbl, dbl, pu8, i64, i32, i32, vp, sz, vp, u32]
     L.wb200_dwt_filter_host.argtypes = [vp, vp, i32, p64, i64, pd, i32, i32, i32, i32, i32, u32]
     L.wb200_dwt_lifting_host.argtypes = [vp, vp, i32, p64, i64, pst, i32, dbl, dbl, i32, i32, i32, i32, u32]
+    L.wb200_modwt.argtypes = [vp, vp, i64, i64, pd, i32, i32, i32, vp, sz, vp, u32]
+    L.wb200_imodwt.argtypes = [vp, vp, i64, i64, pd, i32, i32, i32, vp, sz, vp, u32]
+    L.wb200_modwt.restype = i32
+    L.wb200_imodwt.restype = i32
+    L.wb200_maxmodwttransformlevels.argtypes = [i64]
+    L.wb200_maxmodwttransformlevels.restype = i32
     L.wb200_workspace_bytes.argtypes = [i32, i32, p64, i64, i32, i32, u32]
     L.wb200_workspace_bytes.restype = sz
     L.wb200_maxtransformlevels.argtypes = [i64]

@@ -21,7 +21,7 @@ from . import _lib
 from .util import iscube, isvalidtree, maketree, maxtransformlevels, sufficientpoweroftwo
 from .wt import GLS, OrthoFilter
 
-__all__ = ["dwt", "idwt", "dwt_", "idwt_", "wpt", "iwpt", "wpt_", "iwpt_", "dwtc", "idwtc",
+__all__ = ["modwt", "imodwt", "maxmodwttransformlevels", "dwt", "idwt", "dwt_", "idwt_", "wpt", "iwpt", "wpt_", "iwpt_", "dwtc", "idwtc",
            "dwt_oop_", "idwt_oop_", "ArgumentError", "DimensionMismatch", "set_strict_fp", "colmajor"]
 
 
@@ -320,3 +320,56 @@ def wpt_(*args):
 
 def iwpt_(*args):
     return _xwpt_bang(args, False)
+
+
+# ---- maximal-overlap DWT (src/Transforms/transforms_maximal_overlap.jl) ------------------------------------
+def maxmodwttransformlevels(x) -> int:
+    """floor(log2(length(x))) -- src/Util/non_dyadic.jl:24-25."""
+    n = int(x) if isinstance(x, (int, np.integer)) else int(x.shape[0])
+    return int(np.floor(np.log2(n)))
+
+
+def modwt(x, wt, L=None):
+    """modwt(x, wt[, L]) -> n x (L+1) matrix [W_1 .. W_L V_L] (for an (n, B) batch: (n, L+1, B))."""
+    if not isinstance(wt, OrthoFilter):
+        raise TypeError("modwt takes an OrthoFilter")
+    x = _prep(x)
+    if x.dtype not in (torch.float32, torch.float64) or x.dim() not in (1, 2):
+        raise TypeError("modwt takes a real vector (or an (n, B) batch of columns)")
+    n = int(x.shape[0])
+    B = 1 if x.dim() == 1 else int(x.shape[1])
+    if L is None:
+        L = maxmodwttransformlevels(n)
+    if L > maxmodwttransformlevels(n):
+        raise ArgumentError("Too many transform levels (length(x) < 2^L)")
+    if L < 1:
+        raise ArgumentError("L must be >= 1")
+    shape = (n, L + 1) if x.dim() == 1 else (n, L + 1, B)
+    y = torch.empty_strided(shape, _colmajor_strides(shape), dtype=x.dtype, device=x.device)
+    if x.numel():
+        q, qp = _qmf(wt)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().wb200_modwt(y.data_ptr(), x.data_ptr(), n, B, qp, len(q), int(L), _DTYPES[x.dtype], None, 0,
+                                        _stream(x), _flags)
+        _check(rc)
+    return y
+
+
+def imodwt(xw, wt):
+    """imodwt(xw, wt): the inverse of modwt (xw: n x (L+1), or (n, L+1, B))."""
+    if not isinstance(wt, OrthoFilter):
+        raise TypeError("imodwt takes an OrthoFilter")
+    xw = _prep(xw)
+    if xw.dtype not in (torch.float32, torch.float64) or xw.dim() not in (2, 3):
+        raise TypeError("imodwt takes an n x (L+1) real matrix (or an (n, L+1, B) batch)")
+    n, ncols = int(xw.shape[0]), int(xw.shape[1])
+    B = 1 if xw.dim() == 2 else int(xw.shape[2])
+    shape = (n,) if xw.dim() == 2 else (n, B)
+    x = torch.empty_strided(shape, _colmajor_strides(shape), dtype=xw.dtype, device=xw.device)
+    if xw.numel():
+        q, qp = _qmf(wt)
+        with torch.cuda.device(xw.device):
+            rc = _lib.lib().wb200_imodwt(x.data_ptr(), xw.data_ptr(), n, B, qp, len(q), ncols, _DTYPES[xw.dtype], None, 0,
+                                         _stream(xw), _flags)
+        _check(rc)
+    return x
