@@ -352,7 +352,7 @@ def main():
 
 def run_extras(L, wb, _lib, dev, stream, args):
     """Secondary workloads of BASELINE.json (reported next to the headline, same CUDA-event timing, fewer steps):
-    configs[2] 2-D cdf97 lifting 4096^2 Float32 L=8 (a batch of 16 images so that the working set exceeds L2),
+    configs[2] 2-D cdf97 lifting 4096^2 Float32 L=8 (a batch of 64 images: fills the device, working set >> L2),
     configs[4] 2-D db4 filter bank on the same batch and 3-D db6 512^3 (L=3, the level count of the reference's own
     3-D benchmarks), configs[3] full wavelet-packet tree sym8 N=2^16 (batch 1024).  Fractions are of the measured HBM
     peak with the compulsory byte model (2*sizeof(T) per sample per direction)."""
@@ -363,13 +363,20 @@ def run_extras(L, wb, _lib, dev, stream, args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    k = max(3, min(args.steps, 5))
-
-    def timed_pair(fwd, inv):
-        for _ in range(2):
-            inv(fwd())
-        torch.cuda.synchronize(dev)
+    def timed_pair(fwd, inv, min_ms=150.0):
+        """>= 3 warm-up pairs and >= min_ms of warm-up work (the SM clock needs tens of ms under load to settle), then
+        enough pairs for >= min_ms of timed work (at least 5)."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(3):
+            inv(fwd())
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        per = max(e0.elapsed_time(e1) / 3, 1e-3)
+        for _ in range(int(min(200, max(0, min_ms / per - 3)))):
+            inv(fwd())
+        k = int(min(400, max(5, min_ms / per)))
+        torch.cuda.synchronize(dev)
         e0.record(stream)
         for _ in range(k):
             inv(fwd())
@@ -385,7 +392,7 @@ def run_extras(L, wb, _lib, dev, stream, args):
         return d
 
     res = {}
-    n2, Bi = 4096, 16
+    n2, Bi = 4096, 64          # "a batch of 64 images to fill the device" (cfg5 shards 128 per GPU)
     x2 = torch.randn((Bi, n2, n2), dtype=torch.float32, device=dev).permute(2, 1, 0)      # column-major (n, n, B)
     wl = wb.wavelet(wb.WT.cdf97, wb.WT.Lifting)
     res["dwt2_cdf97_lifting_4096x4096_f32_L8"] = entry(
@@ -402,6 +409,16 @@ def run_extras(L, wb, _lib, dev, stream, args):
     w8 = wb.wavelet(wb.WT.sym8)
     res["wpt_sym8_fulltree_65536_f32"] = entry((1 << 16) * 1024, 4, timed_pair(lambda: wb.wpt(xp, w8), lambda y: wb.iwpt(y, w8)),
                                                signals=1024, note="16 levels x 16 taps: FP32-pipe bound, not HBM bound")
+    del xp
+    # MODWT / IMODWT, db4, n = 2^20 x 64 signals, L = 10.  Compulsory bytes per direction:
+    # read n + write n (L + 1) elements forward, the reverse inverse.
+    nm, Bm, Lm = 1 << 20, 64, 10
+    xm = torch.randn((Bm, nm), dtype=torch.float32, device=dev).t()
+    ms = timed_pair(lambda: wb.modwt(xm, wf, Lm), lambda W: wb.imodwt(W, wf))
+    gbs = 2.0 * (Lm + 2) * nm * Bm * 4 / (ms * 1e-3) / 1e9
+    res["modwt_db4_1048576_f32_L10"] = {"msamples_per_s_pair": nm * Bm / (ms * 1e-3) / 1e6, "ms_per_pair": ms, "achieved_gbs_pair": gbs,
+                                        "frac_of_hbm_peak": gbs / peak, "signals": Bm,
+                                        "note": "bytes = 2 (L + 2) n B sizeof(T): the transform is (L + 1)-fold redundant"}
     return res
 
 

@@ -593,8 +593,11 @@ def test_modwt_vs_oracle(dev, mode, dtype, wname, n, L):
     refb = orc.imodwt(ref, q)
     if mode == "strict":
         assert np.array_equal(to_np(back), refb)
+    # the round trip is as exact as the tabulated filter is orthogonal (coif4: ~1e-10 per level): the bar is the oracle's
     tol = (5e-6 if dtype == np.float32 else 1e-11) * max(1.0, scale)
-    assert np.max(np.abs(to_np(back).astype(np.float64) - x)) <= tol
+    ref_rt = float(np.max(np.abs(refb.astype(np.float64) - x)))
+    assert np.max(np.abs(to_np(back).astype(np.float64) - x)) <= max(tol, 2.0 * ref_rt)
+    assert np.max(np.abs(to_np(back).astype(np.float64) - refb)) <= tol * ref.shape[1]
 
 
 def test_modwt_batch_partial_levels_and_errors(dev):

@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""Per-kernel timing of the 2-D cdf97 lifting workload (4096^2, L=8) through the library's profiling hook."""
+"""Per-kernel timing of the 2-D cdf97 lifting workload (4096^2, L=8) through the library's profiling hook,
+plus a per-depth sweep (L = 1..8) with CUDA events: the difference between consecutive depths is the cost of a level.
+usage: bench2d.py [B_f32 [B_f64]] [--sweep]"""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -7,7 +9,25 @@ import wavelets_b200 as wb
 from wavelets_b200 import _lib
 L = _lib.lib()
 wl = wb.wavelet(wb.WT.cdf97, wb.WT.Lifting)
-for dt, B in ((torch.float32, 16), (torch.float64, 8)):
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+Bf32 = int(args[0]) if len(args) > 0 else 16
+Bf64 = int(args[1]) if len(args) > 1 else 8
+sweep = "--sweep" in sys.argv
+
+
+def timed(fn, reps=5):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fn(); torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+for dt, B in ((torch.float32, Bf32), (torch.float64, Bf64)):
+    if B <= 0:
+        continue
     x = torch.randn((B, 4096, 4096), dtype=dt, device='cuda').permute(2, 1, 0)
     for _ in range(2):
         y = wb.dwtc(x, wl, 8); xr = wb.idwtc(y, wl, 8)
@@ -23,6 +43,16 @@ for dt, B in ((torch.float32, 16), (torch.float64, 8)):
     esz = x.element_size(); bytes_pass = 2 * esz * 4096 * 4096 * B
     fwd = sum(v[1] for k, v in tot.items() if 'fwd' in k or 'forward' in k or 'analysis' in k)
     inv = sum(v[1] for k, v in tot.items() if 'inv' in k or 'synthesis' in k)
-    print(dt, tot)
+    print(dt, 'B', B, tot)
     print('  fwd GB/s', round(bytes_pass / fwd / 1e6, 1), 'inv GB/s', round(bytes_pass / inv / 1e6, 1), 'pair GB/s',
-          round(2 * bytes_pass / (fwd + inv) / 1e6, 1), 'rt', float((xr - x).abs().max()))
+          round(2 * bytes_pass / (fwd + inv) / 1e6, 1), 'rt', float((xr - x).abs().max()), flush=True)
+    if sweep:
+        prev = (0.0, 0.0)
+        for lv in range(1, 9):
+            tf = timed(lambda: wb.dwtc(x, wl, lv))
+            yy = wb.dwtc(x, wl, lv)
+            ti = timed(lambda: wb.idwtc(yy, wl, lv))
+            print(f'  L={lv}: fwd {tf:.4f} ms (+{tf - prev[0]:.4f})  inv {ti:.4f} ms (+{ti - prev[1]:.4f})  pair GB/s {2 * bytes_pass / (tf + ti) / 1e6:.1f}', flush=True)
+            prev = (tf, ti)
+    del x, y, xr
+    torch.cuda.empty_cache()

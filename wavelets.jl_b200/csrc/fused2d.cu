@@ -618,7 +618,14 @@ static int32_t launch_level(const T *a, int64_t lda, int64_t bsa, const T *xd, i
                             T *o1, int64_t ld1, int64_t bs1, T *o2, int64_t ld2, int64_t bs2,
                             int n, int64_t B, const LiftCoefs<T> &lc, cudaStream_t st) {
     // ---- preferred: tensor-map TMA tiles (persistent double-buffered CTAs when there are enough tiles) ----
-    if (env_int2("WB200_LIFT2D_TMA", 1)) {
+    // the TMA kernels move 16-byte pieces to and from global memory: every base and leading dimension must keep that
+    // alignment (always true for the library's scratch and for arrays from a CUDA allocator; a caller's odd sub-view
+    // takes the cp.async kernels below, which use element-wise global accesses)
+    auto al16 = [](const void *q, int64_t ld, int64_t bs) {
+        return q == nullptr || ((reinterpret_cast<uintptr_t>(q) & 15) == 0 && (ld * (int64_t)sizeof(T)) % 16 == 0 && (bs * (int64_t)sizeof(T)) % 16 == 0);
+    };
+    const bool aligned = al16(a, lda, bsa) && al16(xd, ldx, bsx) && al16(o1, ld1, bs1) && al16(o2, ld2, bs2);
+    if (aligned && env_int2("WB200_LIFT2D_TMA", 1)) {
         using C3 = Cfg3For<S, T>;
         const int nx = n / C3::TI, ny = n / C3::TJ;
         const int64_t ntiles64 = (int64_t)nx * ny * B;

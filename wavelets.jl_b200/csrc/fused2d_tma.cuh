@@ -480,8 +480,13 @@ k_lift2d_fwd_tma(const __grid_constant__ TensorMap tm_src, const T *__restrict__
             lift_regs<T, S, STRICT, C::NPJ>(s, d, lc, wrapi(jp0, nh), nh, STRICT && edge_j);
 #pragma unroll
             for (int pp = C::HL; pp < C::HL + C::SJ; ++pp) {
-                Sm[(2 * (q * C::SJ + pp)) * C::PI + il] = fp::mul(s[pp], lc.n1);
-                Sm[(2 * (q * C::SJ + pp) + 1) * C::PI + il] = fp::mul(d[pp], lc.n2);
+                if constexpr (STRICT) {
+                    Sm[(2 * (q * C::SJ + pp)) * C::PI + il] = fp::mul(s[pp], lc.n1);
+                    Sm[(2 * (q * C::SJ + pp) + 1) * C::PI + il] = fp::mul(d[pp], lc.n2);
+                } else {                                  // fast mode: the row factor rides in the dim-1 pass below
+                    Sm[(2 * (q * C::SJ + pp)) * C::PI + il] = s[pp];
+                    Sm[(2 * (q * C::SJ + pp) + 1) * C::PI + il] = d[pp];
+                }
             }
         }
         __syncthreads();
@@ -503,35 +508,63 @@ k_lift2d_fwd_tma(const __grid_constant__ TensorMap tm_src, const T *__restrict__
         __syncthreads();
         if (act) {
             lift_regs<T, S, STRICT, C::NPI>(s, d, lc, wrapi((i0 >> 1) - C::HL + q * C::SI, nh), nh, STRICT && edge_i);
-            T o[2 * C::SI];
+            T os[C::SI], od[C::SI];
+            T f1 = lc.n1, f2 = lc.n2;
+            if constexpr (!STRICT) {                      // fast mode: (row factor) x (column factor) in one multiply
+                const T rowf = (r & 1) ? lc.n2 : lc.n1;   // 2*HL is even: staged row parity = dim-2 parity
+                f1 = lc.n1 * rowf;
+                f2 = lc.n2 * rowf;
+            }
 #pragma unroll
             for (int pp = 0; pp < C::SI; ++pp) {
-                o[2 * pp] = fp::mul(s[C::HL + pp], lc.n1);
-                o[2 * pp + 1] = fp::mul(d[C::HL + pp], lc.n2);
+                os[pp] = fp::mul(s[C::HL + pp], f1);
+                od[pp] = fp::mul(d[C::HL + pp], f2);
             }
-            sts16<T, 2 * C::SI>(Sm + r * C::PI + C::HLS + 2 * q * C::SI, o);   // HLS is a vector multiple: aligned
+            // de-interleaved: the row's s-part at [HLS, HLS + TIp), its d-part behind it (every window of this row was
+            // read before the barrier above), so the store phase moves whole 16-byte pieces
+            sts16<T, C::SI>(Sm + r * C::PI + C::HLS + q * C::SI, os);
+            sts16<T, C::SI>(Sm + r * C::PI + C::HLS + C::TIp + q * C::SI, od);
         }
         __syncthreads();
     }
-    // ---- stores: a thread reads one 16-byte piece of an owned row and writes its s-part and d-part ----
+    // ---- stores: a group of VPR lanes keeps one dim-2 parity and one 16-byte piece column and walks the tile's dim-2
+    //      pairs, so every address is "previous + constant" (the index arithmetic of a flat loop was 38 % of the
+    //      kernel's instructions); the shared-memory reads of a batch are issued before its stores.
     {
         T *llb = ll + (int64_t)b * bs_ll;
         T *yb = yd + (int64_t)b * bs_y;
-        constexpr int VPR = C::TI / C::V;                 // vectors per owned row
-        for (int idx = tid; idx < C::TJ * VPR; idx += C::NT) {
-            const int t = idx % VPR, rr = idx / VPR;
-            const int j = j0 + rr, jq = j >> 1, pj = j & 1;
-            T w[C::V];
-            lds16<T, C::V>(w, Sm + (2 * C::HL + rr) * C::PI + C::HLS + t * C::V);
-            const int ip = (i0 >> 1) + t * (C::V / 2);
+        constexpr int VPR = C::TIp / C::V;                // 16-byte pieces per half row
+        constexpr int G = (C::NT / VPR) & ~1;             // lane groups (even: half of them per dim-2 parity)
+        static_assert(G >= 2 && C::TIp % C::V == 0, "store phase needs two lane groups");
+        constexpr int GH = G / 2;
+        constexpr int NIT = (C::TJp + GH - 1) / GH;
+        constexpr int UB = 2;
+        const int t = tid % VPR, g = tid / VPR;
+        if (g < G) {
+            const int pj = g & 1, q0 = g >> 1;
+            const int ip = (i0 >> 1) + t * C::V;
+            const int jq = (j0 >> 1) + q0;
             T *ps = (pj == 0) ? (llb + (int64_t)jq * ld_ll + ip) : (yb + (int64_t)(nh + jq) * ld_y + ip);
             T *pd = yb + (int64_t)(pj * nh + jq) * ld_y + nh + ip;
-            if constexpr (sizeof(T) == 4) {
-                *reinterpret_cast<float2 *>(ps) = make_float2(w[0], w[2]);
-                *reinterpret_cast<float2 *>(pd) = make_float2(w[1], w[3]);
-            } else {
-                ps[0] = w[0];
-                pd[0] = w[1];
+            const int64_t step_s = (int64_t)GH * ((pj == 0) ? ld_ll : ld_y), step_d = (int64_t)GH * ld_y;
+            const T *sp = Sm + (2 * C::HL + 2 * q0 + pj) * C::PI + C::HLS + t * C::V;
+#pragma unroll
+            for (int it0 = 0; it0 < NIT; it0 += UB) {
+                T ws[UB][C::V], wd[UB][C::V];
+#pragma unroll
+                for (int u = 0; u < UB; ++u)
+                    if (it0 + u < NIT && (C::TJp % GH == 0 || q0 + (it0 + u) * GH < C::TJp)) {
+                        lds16<T, C::V>(ws[u], sp + (it0 + u) * 2 * GH * C::PI);
+                        lds16<T, C::V>(wd[u], sp + (it0 + u) * 2 * GH * C::PI + C::TIp);
+                    }
+#pragma unroll
+                for (int u = 0; u < UB; ++u)
+                    if (it0 + u < NIT && (C::TJp % GH == 0 || q0 + (it0 + u) * GH < C::TJp)) {
+                        sts16<T, C::V>(ps, ws[u]);        // (generic 16-byte store helper: global pointers are fine)
+                        sts16<T, C::V>(pd, wd[u]);
+                        ps += step_s;
+                        pd += step_d;
+                    }
             }
         }
     }
@@ -591,28 +624,38 @@ k_lift2d_inv_tma(const __grid_constant__ TensorMap tm_ll, const __grid_constant_
         T s[C::NPI], d[C::NPI];
         const bool act = tid < C::COL_TASKS_I;
         constexpr int OFF = C::CO - C::HL;
-        T *As = Sm, *Ad = Sm;
+        T *Ao = Sm;
         int q = 0;
         if (act) {
             const int ql = tid % C::JQ;
             const int rest = tid / C::JQ;
             const int pj = rest & 1;
             q = rest >> 1;
-            As = Sm + (0 * 2 + pj) * QSZ + ql * C::PC + q * C::SI;
-            Ad = Sm + (1 * 2 + pj) * QSZ + ql * C::PC + q * C::SI;
+            constexpr int SPH = C::TIp / (2 * C::SI);     // merged segments per quadrant-array row
+            static_assert(C::TIp % (2 * C::SI) == 0, "merged segments must tile a quadrant row");
+            const T *As = Sm + (0 * 2 + pj) * QSZ + ql * C::PC + q * C::SI;
+            const T *Ad = Sm + (1 * 2 + pj) * QSZ + ql * C::PC + q * C::SI;
+            Ao = Sm + ((q / SPH) * 2 + pj) * QSZ + ql * C::PC + C::CO + (q % SPH) * 2 * C::SI;
             lds16<T, C::WINI>(ws, As);
             lds16<T, C::WINI>(wd, Ad);
 #pragma unroll
-            for (int pp = 0; pp < C::NPI; ++pp) { s[pp] = fp::mul(ws[OFF + pp], lc.n1); d[pp] = fp::mul(wd[OFF + pp], lc.n2); }
+            T f1 = lc.n1, f2 = lc.n2;
+            if constexpr (!STRICT) {                      // fast mode: both (reciprocal) factors of a quadrant in one multiply
+                const T rowf = pj ? lc.n2 : lc.n1;
+                f1 = lc.n1 * rowf;
+                f2 = lc.n2 * rowf;
+            }
+            for (int pp = 0; pp < C::NPI; ++pp) { s[pp] = fp::mul(ws[OFF + pp], f1); d[pp] = fp::mul(wd[OFF + pp], f2); }
         }
         __syncthreads();
         if (act) {
             lift_regs<T, S, STRICT, C::NPI>(s, d, lc, wrapi(ip0 - C::HL + q * C::SI, nh), nh, STRICT && edge_i);
-            T os[C::SI], od[C::SI];
+            T o[2 * C::SI];
 #pragma unroll
-            for (int pp = 0; pp < C::SI; ++pp) { os[pp] = s[C::HL + pp]; od[pp] = d[C::HL + pp]; }
-            sts16<T, C::SI>(As + C::CO, os);
-            sts16<T, C::SI>(Ad + C::CO, od);
+            for (int pp = 0; pp < C::SI; ++pp) { o[2 * pp] = s[C::HL + pp]; o[2 * pp + 1] = d[C::HL + pp]; }
+            // merged (interleaved) along dim 1 already here: output sample i of this row lives in array (i / TIp, pj) at
+            // column CO + i % TIp -- the dim-2 pass below only needs the two pj arrays to agree on the column labels
+            sts16<T, 2 * C::SI>(Ao, o);
         }
         __syncthreads();
     }
@@ -630,7 +673,10 @@ k_lift2d_inv_tma(const __grid_constant__ TensorMap tm_ll, const __grid_constant_
             A0 = Sm + (pi * 2 + 0) * QSZ + (q * C::SJ) * C::PC + c;
             A1 = Sm + (pi * 2 + 1) * QSZ + (q * C::SJ) * C::PC + c;
 #pragma unroll
-            for (int pp = 0; pp < C::NPJ; ++pp) { s[pp] = fp::mul(A0[pp * C::PC], lc.n1); d[pp] = fp::mul(A1[pp * C::PC], lc.n2); }
+            for (int pp = 0; pp < C::NPJ; ++pp) {
+                if constexpr (STRICT) { s[pp] = fp::mul(A0[pp * C::PC], lc.n1); d[pp] = fp::mul(A1[pp * C::PC], lc.n2); }
+                else                  { s[pp] = A0[pp * C::PC]; d[pp] = A1[pp * C::PC]; }      // scaled in the dim-1 pass
+            }
         }
         __syncthreads();
         if (act) {
@@ -640,25 +686,36 @@ k_lift2d_inv_tma(const __grid_constant__ TensorMap tm_ll, const __grid_constant_
         }
         __syncthreads();
     }
-    // ---- merged store: out[2ip + pi, 2jq + pj] ----
+    // ---- store: the rows are already merged along dim 1; a group of VPR lanes keeps one dim-2 parity and one 16-byte
+    //      piece column and walks the tile's dim-2 pairs (every address is "previous + constant").
     {
         T *db = dst + (int64_t)b * bs_d;
-        constexpr int VPR = C::TIp / C::V;                // 16-byte pieces per owned quadrant row
-        for (int idx = tid; idx < 2 * C::TJp * VPR; idx += C::NT) {
-            const int t = idx % VPR;
-            const int rest = idx / VPR;
-            const int pj = rest & 1, qq = rest >> 1;       // owned dim-2 pair qq
-            const int ql = C::HL + qq;
-            T ws[C::V], wd[C::V];
-            lds16<T, C::V>(ws, Sm + (0 * 2 + pj) * QSZ + ql * C::PC + C::CO + t * C::V);
-            lds16<T, C::V>(wd, Sm + (1 * 2 + pj) * QSZ + ql * C::PC + C::CO + t * C::V);
-            T *p = db + (int64_t)(2 * (jq0 + qq) + pj) * ld_d + 2 * (ip0 + t * C::V);
-            if constexpr (sizeof(T) == 4) {
-                *reinterpret_cast<float4 *>(p) = make_float4(ws[0], wd[0], ws[1], wd[1]);
-                *reinterpret_cast<float4 *>(p + 4) = make_float4(ws[2], wd[2], ws[3], wd[3]);
-            } else {
-                *reinterpret_cast<double2 *>(p) = make_double2(ws[0], wd[0]);
-                *reinterpret_cast<double2 *>(p + 2) = make_double2(ws[1], wd[1]);
+        constexpr int VPR = C::TI / C::V;                 // pieces per output row
+        constexpr int VPH = C::TIp / C::V;                // pieces per quadrant-array row
+        constexpr int G = (C::NT / VPR) & ~1;
+        static_assert(G >= 2, "store phase needs two lane groups");
+        constexpr int GH = G / 2;
+        constexpr int NIT = (C::TJp + GH - 1) / GH;
+        constexpr int UB = 4;
+        const int t = tid % VPR, g = tid / VPR;
+        if (g < G) {
+            const int pj = g & 1, q0 = g >> 1;
+            const T *sp = Sm + ((t / VPH) * 2 + pj) * QSZ + (C::HL + q0) * C::PC + C::CO + (t % VPH) * C::V;
+            T *p = db + (int64_t)(2 * (jq0 + q0) + pj) * ld_d + 2 * ip0 + t * C::V;
+            const int64_t step = (int64_t)2 * GH * ld_d;
+#pragma unroll
+            for (int it0 = 0; it0 < NIT; it0 += UB) {
+                T w[UB][C::V];
+#pragma unroll
+                for (int u = 0; u < UB; ++u)
+                    if (it0 + u < NIT && (C::TJp % GH == 0 || q0 + (it0 + u) * GH < C::TJp))
+                        lds16<T, C::V>(w[u], sp + (it0 + u) * GH * C::PC);
+#pragma unroll
+                for (int u = 0; u < UB; ++u)
+                    if (it0 + u < NIT && (C::TJp % GH == 0 || q0 + (it0 + u) * GH < C::TJp)) {
+                        sts16<T, C::V>(p, w[u]);
+                        p += step;
+                    }
             }
         }
     }
