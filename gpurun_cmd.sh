@@ -1,9 +1,13 @@
 #!/bin/bash
-# scratch: GPU validation of MODWT + the reworked 2-D level kernels
 cd /root/repo
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu -k "modwt or lift2d or full_size_2d or golden or lifting" 2>&1 | tail -15 > gpurun_out/pytest_part.log
+timeout 900 python -m pytest tests -x -q -m gpu -k "wpt" 2>&1 | tail -8 > gpurun_out/pytest_part.log
 cat gpurun_out/pytest_part.log
-timeout 300 python tools/bench2d.py 16 8 --sweep > gpurun_out/bench2d.log 2>&1; cat gpurun_out/bench2d.log
-timeout 300 python tools/bench2d.py 64 0 > gpurun_out/bench2d_b64.log 2>&1; cat gpurun_out/bench2d_b64.log
-timeout 300 python tools/bench_modwt.py > gpurun_out/bench_modwt.log 2>&1; cat gpurun_out/bench_modwt.log
+timeout 300 python tools/bench_nd.py > gpurun_out/bench_nd.log 2>&1; cat gpurun_out/bench_nd.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_f32.log 2> gpurun_out/bench.err; python - <<'PY'
+import json
+d=json.loads(open('/root/repo/gpurun_out/bench_f32.log').read().strip().splitlines()[-1])
+print('value',d['value'],'frac',d['roofline']['frac'],'e2e',d['e2e']['value'])
+for k,v in d.get('extras',{}).items(): print(k, round(v['ms_per_pair'],3),'ms', round(v['achieved_gbs_pair'],1),'GB/s', round(v['frac_of_hbm_peak'],4))
+PY
+tail -5 gpurun_out/bench.err

@@ -524,8 +524,9 @@ def test_fused_lift2d_vs_oracle(dev, mode, dtype, wname, n, L, B):
 # ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("wname", ["haar", "db2", "db4", "db6", "sym8", "db10"])
-def test_fastpass_nd_filter_vs_oracle(dev, mode, dtype, wname):
+def test_fastpass_nd_filter_vs_oracle(dev, mode, dtype, wname, monkeypatch):
     from wavelets_b200 import _lib
+    monkeypatch.setenv("WB200_DISABLE_FIR2D", "1")     # the fused 2-D level kernels would take the square cases
     wt = wavelet(wavelet_class(wname))
     for shape, L in (((256, 128), 3), ((512, 512), 2), ((64, 64, 64), 2), ((128, 32, 64), 1)):
         x = rng(sum(shape) + L).standard_normal(shape).astype(dtype)
@@ -637,3 +638,64 @@ def test_modwt_large_batch_energy(dev):
     e0, e1 = float((x ** 2).sum()), float((W ** 2).sum())
     assert abs(e1 - e0) <= 1e-10 * e0
     assert float((wb.imodwt(W, wt) - x).abs().max()) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused 2-D filter-bank level kernels (fir2d_impl.cuh): every supported filter length, both tile configurations
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("wname", ["haar", "db2", "db3", "db4", "db5", "db6", "db7", "sym8", "db9", "db10", "coif2", "beyl"])
+def test_fused_fir2d_vs_oracle(dev, mode, dtype, wname):
+    from wavelets_b200 import _lib
+    wt = wavelet(wavelet_class(wname))
+    for n, L, B in ((128, 1, 1), (256, 3, 2), (384, 2, 1)):
+        x = rng(n + L + B).standard_normal((n, n, B)).astype(dtype)
+        _lib.lib().wb200_profile_enable(1)
+        y = wb.dwtc(to_gpu(x, dev), wt, L)
+        xr = wb.idwtc(y, wt, L)
+        _lib.lib().wb200_profile_enable(0)
+        names = _kernel_names()
+        assert {"fused_fir2d_fwd", "fused_fir2d_inv"} <= names, names
+        check(y, orc.dwt_filter_batch(x, 2, wt.qmf, L), mode, 2 * L, 8.0)
+        check(xr, orc.dwt_filter_batch(to_np(y), 2, wt.qmf, L, fw=False), mode, 2 * L, 8.0)
+    # plain 2-D call (no batch dimension), out-of-place dwt! form
+    x = rng(5).standard_normal((256, 256)).astype(dtype)
+    y = wb.dwt(to_gpu(x, dev), wt, 2)
+    check(y, orc.dwt_filter(x, wt.qmf, 2), mode, 4, 8.0)
+    check(wb.idwt(y, wt, 2), orc.dwt_filter(to_np(y), wt.qmf, 2, fw=False), mode, 4, 8.0)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_full_size_2d_db4(dev, dtype):
+    """BASELINE config 5 shape (4096^2 images, db4 filter bank, L=8): size-independent properties"""
+    wt = wavelet(WT.db4)
+    x = torch.randn((2, 4096, 4096), dtype=dtype, device=dev).permute(2, 1, 0)
+    y = wb.dwtc(x, wt, 8)
+    e0, e1 = float((x.double() ** 2).sum()), float((y.double() ** 2).sum())
+    assert abs(e1 - e0) <= (1e-5 if dtype == torch.float32 else 1e-11) * e0        # orthogonal transform
+    xr = wb.idwtc(y, wt, 8)
+    assert float((xr - x).abs().max()) < (2e-4 if dtype == torch.float32 else 1e-10)
+    # linearity: T(2x) == 2 T(x) exactly (power-of-two scaling commutes with every rounding)
+    assert torch.equal(wb.dwtc(2 * x, wt, 8), 2 * y)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("wname", ["haar", "db4", "db6", "sym8", "db10"])
+def test_fused_fir3d_vs_oracle(dev, mode, dtype, wname):
+    """3-D filter bank: dim-3 line pass + ONE fused (dim 2, dim 1) launch per level on volumes with square faces"""
+    from wavelets_b200 import _lib
+    wt = wavelet(wavelet_class(wname))
+    for shape, L in (((128, 128, 8), 1), ((256, 256, 4), 2), ((128, 128, 16), 3)):
+        x = rng(sum(shape) + L).standard_normal(shape).astype(dtype)
+        _lib.lib().wb200_profile_enable(1)
+        y = wb.dwt(to_gpu(x, dev), wt, L)
+        xr = wb.idwt(y, wt, L)
+        _lib.lib().wb200_profile_enable(0)
+        names = _kernel_names()
+        assert {"fused_fir2d_fwd", "fused_fir2d_inv"} <= names, names
+        check(y, orc.dwt_filter(x, wt.qmf, L), mode, 3 * L, 8.0)
+        check(xr, orc.dwt_filter(to_np(y), wt.qmf, L, fw=False), mode, 3 * L, 8.0)
+    xb = rng(3).standard_normal((128, 128, 4, 2)).astype(dtype)          # two volumes
+    yb = wb.dwtc(to_gpu(xb, dev), wt, 2)
+    check(yb, orc.dwt_filter_batch(xb, 3, wt.qmf, 2), mode, 6, 8.0)
+    check(wb.idwtc(yb, wt, 2), orc.dwt_filter_batch(to_np(yb), 3, wt.qmf, 2, fw=False), mode, 6, 8.0)

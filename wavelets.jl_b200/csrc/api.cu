@@ -88,6 +88,24 @@ static bool isvalidtree(int64_t n, const uint8_t *b, int64_t nb) {
 // ---------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t b) { return (b + 255) & ~(size_t)255; }
 
+// The stream-ordered pool returns freed memory to the OS at the next synchronisation unless told otherwise; a transform
+// called in a loop would then re-map its scratch (milliseconds per GB) on every call.  Raise the release threshold of the
+// device's default pool once per device: scratch stays reserved for reuse (cudaMemPoolTrimTo releases it on request).
+void keep_pool_memory() {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { (void)cudaGetLastError(); return; }
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[dev]) return;
+    done[dev] = true;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t thr = ~0ull;
+        if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr) != cudaSuccess) (void)cudaGetLastError();
+    } else (void)cudaGetLastError();
+}
+
 struct Workspace {
     char *base = nullptr;
     size_t size = 0, used = 0;
@@ -104,6 +122,7 @@ struct Workspace {
             base = (char *)user; size = user_bytes;
             return WB200_OK;
         }
+        keep_pool_memory();
         if (!cuda_ok(cudaMallocAsync((void **)&base, need, stream), "cudaMallocAsync(workspace)")) return WB200_ECUDA;
         size = need; owned = true;
         return WB200_OK;
@@ -264,16 +283,54 @@ static int32_t run_nd(const PassOp<T> &op, T *y, const T *x, const ArrayGeom &g,
         if (!W[q]) { set_error("internal: N-D workspace plan mismatch"); return WB200_EWORKSPACE; }
     }
     const int nlev = l_hi - l_lo + 1;
+    // 3-D filter bank on a volume whose (dim 1, dim 2) faces are squares the tile kernels take: the dim-2 and dim-1
+    // passes of a level run as ONE fused 2-D launch per volume over the corner's planes (fir2d_impl.cuh), so a level is
+    // two passes over the corner instead of three
+    const bool fuse3_base = nd == 3 && !op.lifting && !op.generic_only && g.C == 1 && g.dim[0] == g.dim[1] && g.batch <= 16 &&
+                            fir2d_tile_edge<T>(op.fc.F) > 0 && fir2d_available<T>() && std::getenv("WB200_DISABLE_FIR2D") == nullptr &&
+                            ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(W[0])) & 15) == 0;
     for (int it = 0; it < nlev; ++it) {
         const int l = fw ? l_lo + it : l_hi - it;
         int64_t cor[3];
         for (int a = 0; a < 3; ++a) cor[a] = (a < nd) ? (g.dim[a] >> (l - 1)) : 1;
+        const int te = fuse3_base ? fir2d_tile_edge<T>(op.fc.F) : 0;
+        const bool fuse3 = fuse3_base && cor[0] >= te && cor[0] % te == 0 && cor[2] >= 2 && cor[2] <= 65535;
+        const int64_t plane = g.dim[0] * g.dim[1], wplane = gw.dim[0] * gw.dim[1];
         for (int p = 0; p < nd; ++p) {
             const int ax = fw ? nd - p : p + 1;
+            if (fuse3 && fw && p == 1) {          // planes of W[0] -> quadrants of y's planes
+                for (int64_t b = 0; b < g.batch; ++b) {
+                    T *yb = y + b * g.slice();
+                    const int32_t rc = fir2d_level<T>(op, true, W[0] + b * gw.slice(), gw.dim[0], wplane, nullptr, 0, 0,
+                                                      yb, g.dim[0], plane, yb, g.dim[0], plane, (int)cor[0], cor[2], op.st);
+                    if (rc != WB200_OK) return rc;
+                }
+                break;
+            }
+            if (fuse3 && !fw && p == 0) {         // quadrants of x's planes (LLL corner from y below level L) -> planes of W[0]
+                const int64_t dh = cor[2] / 2;
+                for (int64_t b = 0; b < g.batch; ++b) {
+                    const T *xb = x + b * g.slice();
+                    const T *yb = y + b * g.slice();
+                    T *wb_ = W[0] + b * gw.slice();
+                    int32_t rc;
+                    if (l < L) {
+                        rc = fir2d_level<T>(op, false, yb, g.dim[0], plane, xb, g.dim[0], plane, wb_, gw.dim[0], wplane, nullptr, 0, 0, (int)cor[0], dh, op.st);
+                        if (rc != WB200_OK) return rc;
+                        rc = fir2d_level<T>(op, false, xb + dh * plane, g.dim[0], plane, xb + dh * plane, g.dim[0], plane,
+                                            wb_ + dh * wplane, gw.dim[0], wplane, nullptr, 0, 0, (int)cor[0], cor[2] - dh, op.st);
+                    } else {
+                        rc = fir2d_level<T>(op, false, xb, g.dim[0], plane, xb, g.dim[0], plane, wb_, gw.dim[0], wplane, nullptr, 0, 0, (int)cor[0], cor[2], op.st);
+                    }
+                    if (rc != WB200_OK) return rc;
+                }
+                p = 1;                            // the dim-2 pass is done too; the dim-3 pass below reads W[0]
+                continue;
+            }
             View<T> vs, vd; Extent e, e2; int64_t thr[4], thr2[4];
             // source of this pass
             if (p == 0) make_lines<T>(g, cor, ax, const_cast<T *>((fw && l > 1) ? y : x), vs, e, thr);
-            else        make_lines<T>(gw, cor, ax, W[p - 1], vs, e, thr);
+            else        make_lines<T>(gw, cor, ax, (fuse3 && !fw) ? W[0] : W[p - 1], vs, e, thr);
             // destination of this pass
             if (p == nd - 1) make_lines<T>(g, cor, ax, y, vd, e2, thr2);
             else             make_lines<T>(gw, cor, ax, W[p], vd, e2, thr2);
@@ -446,7 +503,9 @@ static int32_t dispatch_dwt(PassOp<T> &op, void *y, const void *x, const Call &c
     }
     // 2-D lifting: fused level kernels for the large levels, then the pyramid-tail kernel (or, for shapes it does not
     // take, the generic passes) for the small remainder
-    if (!(flags & WB200_FLAG_FORCE_GENERIC) && g.C == 1 && g.ndim == 2 && lifting) {
+    // (orthogonal filters: tensor-map tile kernels, which move 16-byte pieces -- x and y must keep that alignment)
+    if (!(flags & WB200_FLAG_FORCE_GENERIC) && g.C == 1 && g.ndim == 2 &&
+        (lifting || (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0))) {
         int Lf = 0;
         bool tail = false;
         const size_t need = plan_fused2d<T>(op, c, L, fw, inplace, Lf, tail);

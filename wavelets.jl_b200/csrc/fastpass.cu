@@ -230,40 +230,190 @@ k_walk_syn(View<const T> slo, View<const T> shi, View<const T> salt, int64_t thr
 // ===================================================================================================
 constexpr int WPT_SUB_MAX = 4096;
 
+// The per-level work is FP32-bound (2 F multiply-adds per sample per level), so the shared-memory side has to stay out
+// of the way: a thread computes FOUR consecutive output pairs from register windows filled with conflict-free 16-byte
+// loads.  Analysis reads a sub-node through its two polyphase components -- stored SPLIT, [even samples | odd samples],
+// by the level above (or by the global load) -- so that pair k needs E[k .. k+Q-1], O[k .. k+Q-1] (approximation) and
+// E[k-Q+1 .. k], O[k-Q+1 .. k] (detail), Q = F/2: consecutive lanes read consecutive 16-byte chunks.  The periodic wrap
+// is applied to chunk indices (sub-node half-lengths that are multiples of 4).  Sub-nodes of 4 or 2 samples are one
+// register-resident node per thread with the wrap resolved at compile time; anything else takes the per-pair loop.
+template <typename T> struct Vec4 { T v[4]; };
+template <typename T> __device__ __forceinline__ void ld4(T (&w)[4], const T *p) {
+    if constexpr (sizeof(T) == 4) { const float4 q = *reinterpret_cast<const float4 *>(p); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
+    else { const double2 q0 = *reinterpret_cast<const double2 *>(p), q1 = *reinterpret_cast<const double2 *>(p + 2); w[0] = q0.x; w[1] = q0.y; w[2] = q1.x; w[3] = q1.y; }
+}
+template <typename T> __device__ __forceinline__ void st4(T *p, T a, T b, T c, T d) {
+    if constexpr (sizeof(T) == 4) *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+    else { *reinterpret_cast<double2 *>(p) = make_double2(a, b); *reinterpret_cast<double2 *>(p + 2) = make_double2(c, d); }
+}
+template <typename T> __device__ __forceinline__ void st2(T *p, T a, T b) {
+    if constexpr (sizeof(T) == 4) *reinterpret_cast<float2 *>(p) = make_float2(a, b);
+    else *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+}
+
+// a[k] = sum_t h[t] x[(2k+t) mod ML] (t increasing), d[k] = sum_i g[F-1-i] x[(2k+2-F+i) mod ML] (i increasing): one
+// node of ML in {2, 4} samples in registers, x given as xe[] (even samples) and xo[] (odd samples)
+template <typename T, int F, bool STRICT, int ML>
+__device__ __forceinline__ void tiny_ana(const T (&xe)[ML / 2], const T (&xo)[ML / 2], T (&a)[ML / 2], T (&d)[ML / 2], const Taps<T, F> &c) {
+    using fp = FP<STRICT>;
+    constexpr int NH = ML / 2;
+#pragma unroll
+    for (int k = 0; k < NH; ++k) {
+        T acc = fp::mul(c.h[0], xe[k % NH]);
+#pragma unroll
+        for (int t = 1; t < F; ++t) {
+            const int i = (2 * k + t) % ML;
+            acc = fp::mac(acc, c.h[t], (i & 1) ? xo[i >> 1] : xe[i >> 1]);
+        }
+        a[k] = acc;
+        constexpr int BIG = ML * F;      // keeps the modulus argument non-negative
+        const int i0 = (2 * k + 2 - F + BIG) % ML;
+        T q = fp::mul(c.g[F - 1], (i0 & 1) ? xo[i0 >> 1] : xe[i0 >> 1]);
+#pragma unroll
+        for (int t = 1; t < F; ++t) {
+            const int i = (2 * k + 2 - F + t + BIG) % ML;
+            q = fp::mac(q, c.g[F - 1 - t], (i & 1) ? xo[i >> 1] : xe[i >> 1]);
+        }
+        d[k] = q;
+    }
+}
+// x[2u] / x[2u+1] from the bands a[], d[] of NH in {1, 2} samples (generic_kernels.cu: k_filter_synthesis order)
+template <typename T, int F, bool STRICT, int NH>
+__device__ __forceinline__ void tiny_syn(const T (&a)[NH], const T (&d)[NH], T (&x)[2 * NH], const Taps<T, F> &c) {
+    using fp = FP<STRICT>;
+    constexpr int Q = F / 2;
+    constexpr int BIG = NH * Q;
+#pragma unroll
+    for (int u = 0; u < NH; ++u) {
+        T rae = fp::mul(c.h[2 * (Q - 1)], a[(u - (Q - 1) + BIG) % NH]);
+        T rao = fp::mul(c.h[2 * (Q - 1) + 1], a[(u - (Q - 1) + BIG) % NH]);
+#pragma unroll
+        for (int t = Q - 2; t >= 0; --t) {
+            rae = fp::mac(rae, c.h[2 * t], a[(u - t + BIG) % NH]);
+            rao = fp::mac(rao, c.h[2 * t + 1], a[(u - t + BIG) % NH]);
+        }
+        T rde = fp::mul(c.g[1], d[u % NH]);
+        T rdo = fp::mul(c.g[0], d[u % NH]);
+#pragma unroll
+        for (int t = 1; t < Q; ++t) {
+            rde = fp::mac(rde, c.g[2 * t + 1], d[(u + t) % NH]);
+            rdo = fp::mac(rdo, c.g[2 * t], d[(u + t) % NH]);
+        }
+        x[2 * u] = fp::add(rae, rde);
+        x[2 * u + 1] = fp::add(rao, rdo);
+    }
+}
+
 template <typename T, int F, bool STRICT>
 __global__ void __launch_bounds__(256)
 k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int levels, int64_t nodes,
               const __grid_constant__ Taps<T, F> c) {
     using fp = FP<STRICT>;
+    constexpr int Q = F / 2;
+    constexpr int CL = (Q - 1 + 3) / 4;          // chunks of left / right reach
+    constexpr int NCH = 2 * CL + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *in = reinterpret_cast<T *>(smem_raw);
     T *out = in + m;
     const int64_t q = blockIdx.x % nodes, b = blockIdx.x / nodes;
     const int64_t base = b * n + q * (int64_t)m;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) in[i] = S[base + i];
+    // split load: even samples to [0, m/2), odd samples to [m/2, m)
+    for (int p = threadIdx.x; p < (m >> 1); p += blockDim.x) {
+        in[p] = S[base + 2 * p];
+        in[(m >> 1) + p] = S[base + 2 * p + 1];
+    }
     __syncthreads();
     for (int l = 0; l < levels; ++l) {
         const int ml = m >> l, nh = ml >> 1;
-        for (int idx = threadIdx.x; idx < (m >> 1); idx += blockDim.x) {
-            const int j = idx / nh, k = idx - j * nh;
-            const T *x = in + j * ml;
-            int ia = 2 * k;
-            T a = fp::mul(c.h[0], x[ia]);
+        const bool last = (l == levels - 1);
+        const bool split_out = !last && (nh % 2 == 0);       // the next level wants its sub-nodes split (needs an even length)
+        // (an odd nh can only be followed by no level at all: m % 2^levels == 0)
+        if (nh >= 4 && (nh & 3) == 0) {
+            const int cpn = nh >> 2;                          // chunks per half sub-node
+            for (int idx = threadIdx.x; idx < (m >> 3); idx += blockDim.x) {
+                const int j = idx / cpn, c0 = idx - j * cpn;
+                const T *E = in + j * ml, *O = E + nh;
+                T we[4 * NCH], wo[4 * NCH];
+                int ci = c0 - CL;
+                ci %= cpn; if (ci < 0) ci += cpn;
 #pragma unroll
-            for (int t = 1; t < F; ++t) {
-                if (++ia == ml) ia = 0;
-                a = fp::mac(a, c.h[t], x[ia]);
-            }
-            int id = (2 * k + 2 - F) % ml;
-            if (id < 0) id += ml;
-            T d = fp::mul(c.g[F - 1], x[id]);
+                for (int i = 0; i < NCH; ++i) {
+                    T t4[4];
+                    ld4(t4, E + 4 * ci);
+                    we[4 * i] = t4[0]; we[4 * i + 1] = t4[1]; we[4 * i + 2] = t4[2]; we[4 * i + 3] = t4[3];
+                    ld4(t4, O + 4 * ci);
+                    wo[4 * i] = t4[0]; wo[4 * i + 1] = t4[1]; wo[4 * i + 2] = t4[2]; wo[4 * i + 3] = t4[3];
+                    if (++ci == cpn) ci = 0;
+                }
+                T av[4], dv[4];
 #pragma unroll
-            for (int t = 1; t < F; ++t) {
-                if (++id == ml) id = 0;
-                d = fp::mac(d, c.g[F - 1 - t], x[id]);
+                for (int r = 0; r < 4; ++r) {
+                    T acc = fp::mul(c.h[0], we[4 * CL + r]);
+#pragma unroll
+                    for (int t = 1; t < F; ++t) acc = fp::mac(acc, c.h[t], (t & 1) ? wo[4 * CL + r + (t - 1) / 2] : we[4 * CL + r + t / 2]);
+                    av[r] = acc;
+                    T qd = fp::mul(c.g[F - 1], we[4 * CL + r + 1 - Q]);
+#pragma unroll
+                    for (int t = 1; t < F; ++t) qd = fp::mac(qd, c.g[F - 1 - t], (t & 1) ? wo[4 * CL + r + 1 - Q + (t - 1) / 2] : we[4 * CL + r + 1 - Q + t / 2]);
+                    dv[r] = qd;
+                }
+                T *oa = out + j * ml, *od = oa + nh;
+                const int k0 = 4 * c0;
+                if (split_out) {
+                    const int hh = nh >> 1;
+                    st2(oa + (k0 >> 1), av[0], av[2]); st2(oa + hh + (k0 >> 1), av[1], av[3]);
+                    st2(od + (k0 >> 1), dv[0], dv[2]); st2(od + hh + (k0 >> 1), dv[1], dv[3]);
+                } else {
+                    st4(oa + k0, av[0], av[1], av[2], av[3]);
+                    st4(od + k0, dv[0], dv[1], dv[2], dv[3]);
+                }
             }
-            out[j * ml + k] = a;
-            out[j * ml + nh + k] = d;
+        } else if (ml == 4) {
+            for (int j = threadIdx.x; j < (m >> 2); j += blockDim.x) {
+                T w[4];
+                ld4(w, in + 4 * j);                            // [E0 E1 | O0 O1]
+                const T xe[2] = {w[0], w[1]}, xo[2] = {w[2], w[3]};
+                T a[2], d[2];
+                tiny_ana<T, F, STRICT, 4>(xe, xo, a, d, c);
+                st4(out + 4 * j, a[0], a[1], d[0], d[1]);      // children of 2 samples: split == natural
+            }
+        } else if (ml == 2) {
+            for (int j = threadIdx.x; j < (m >> 1); j += blockDim.x) {
+                const T xe[1] = {in[2 * j]}, xo[1] = {in[2 * j + 1]};
+                T a[1], d[1];
+                tiny_ana<T, F, STRICT, 2>(xe, xo, a, d, c);
+                st2(out + 2 * j, a[0], d[0]);
+            }
+        } else {
+            // any other sub-node length: one pair per thread, modular walk through the split components
+            for (int idx = threadIdx.x; idx < (m >> 1); idx += blockDim.x) {
+                const int j = idx / nh, k = idx - j * nh;
+                const T *E = in + j * ml, *O = E + nh;
+                int ia = 2 * k;
+                T a = fp::mul(c.h[0], E[ia >> 1]);
+#pragma unroll
+                for (int t = 1; t < F; ++t) {
+                    if (++ia == ml) ia = 0;
+                    a = fp::mac(a, c.h[t], (ia & 1) ? O[ia >> 1] : E[ia >> 1]);
+                }
+                int id = (2 * k + 2 - F) % ml;
+                if (id < 0) id += ml;
+                T d = fp::mul(c.g[F - 1], (id & 1) ? O[id >> 1] : E[id >> 1]);
+#pragma unroll
+                for (int t = 1; t < F; ++t) {
+                    if (++id == ml) id = 0;
+                    d = fp::mac(d, c.g[F - 1 - t], (id & 1) ? O[id >> 1] : E[id >> 1]);
+                }
+                T *oa = out + j * ml, *od = oa + nh;
+                if (split_out) {
+                    const int hh = nh >> 1;
+                    oa[(k & 1) * hh + (k >> 1)] = a;
+                    od[(k & 1) * hh + (k >> 1)] = d;
+                } else {
+                    oa[k] = a;
+                    od[k] = d;
+                }
+            }
         }
         __syncthreads();
         T *t = in; in = out; out = t;
@@ -277,6 +427,7 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
               const __grid_constant__ Taps<T, F> c) {
     using fp = FP<STRICT>;
     constexpr int Q = F / 2;
+    constexpr int CL = (Q - 1 + 3) / 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *in = reinterpret_cast<T *>(smem_raw);
     T *out = in + m;
@@ -286,30 +437,97 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
     __syncthreads();
     for (int l = levels - 1; l >= 0; --l) {
         const int ml = m >> l, nh = ml >> 1;
-        for (int idx = threadIdx.x; idx < (m >> 1); idx += blockDim.x) {
-            const int j = idx / nh, u = idx - j * nh;
-            const T *a = in + j * ml, *d = a + nh;
-            int ia = (u - (Q - 1)) % nh;
-            if (ia < 0) ia += nh;
-            T rae = fp::mul(c.h[2 * (Q - 1)], a[ia]);
-            T rao = fp::mul(c.h[2 * (Q - 1) + 1], a[ia]);
+        if (nh >= 4 && (nh & 3) == 0) {
+            // four output pairs per thread: a[u0-Q+1 .. u0+3] and d[u0 .. u0+2+Q] in registers (16-byte chunks, chunk wrap)
+            const int cpn = nh >> 2;
+            for (int idx = threadIdx.x; idx < (m >> 3); idx += blockDim.x) {
+                const int j = idx / cpn, c0 = idx - j * cpn;
+                const T *A = in + j * ml, *Dd = A + nh;
+                T wa[4 * (CL + 1)], wd[4 * (CL + 1)];
+                int ci = c0 - CL;
+                ci %= cpn; if (ci < 0) ci += cpn;
 #pragma unroll
-            for (int t = Q - 2; t >= 0; --t) {
-                if (++ia == nh) ia = 0;
-                rae = fp::mac(rae, c.h[2 * t], a[ia]);
-                rao = fp::mac(rao, c.h[2 * t + 1], a[ia]);
-            }
-            int id = u;
-            T rde = fp::mul(c.g[1], d[id]);
-            T rdo = fp::mul(c.g[0], d[id]);
+                for (int i = 0; i <= CL; ++i) {
+                    T t4[4];
+                    ld4(t4, A + 4 * ci);
+                    wa[4 * i] = t4[0]; wa[4 * i + 1] = t4[1]; wa[4 * i + 2] = t4[2]; wa[4 * i + 3] = t4[3];
+                    if (++ci == cpn) ci = 0;
+                }
+                ci = c0;
 #pragma unroll
-            for (int t = 1; t < Q; ++t) {
-                if (++id == nh) id = 0;
-                rde = fp::mac(rde, c.g[2 * t + 1], d[id]);
-                rdo = fp::mac(rdo, c.g[2 * t], d[id]);
+                for (int i = 0; i <= CL; ++i) {
+                    T t4[4];
+                    ld4(t4, Dd + 4 * ci);
+                    wd[4 * i] = t4[0]; wd[4 * i + 1] = t4[1]; wd[4 * i + 2] = t4[2]; wd[4 * i + 3] = t4[3];
+                    if (++ci == cpn) ci = 0;
+                }
+                T xo[8];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    // a[u - t] = wa[4 CL + r - t]; d[u + t] = wd[r + t]
+                    T rae = fp::mul(c.h[2 * (Q - 1)], wa[4 * CL + r - (Q - 1)]);
+                    T rao = fp::mul(c.h[2 * (Q - 1) + 1], wa[4 * CL + r - (Q - 1)]);
+#pragma unroll
+                    for (int t = Q - 2; t >= 0; --t) {
+                        rae = fp::mac(rae, c.h[2 * t], wa[4 * CL + r - t]);
+                        rao = fp::mac(rao, c.h[2 * t + 1], wa[4 * CL + r - t]);
+                    }
+                    T rde = fp::mul(c.g[1], wd[r]);
+                    T rdo = fp::mul(c.g[0], wd[r]);
+#pragma unroll
+                    for (int t = 1; t < Q; ++t) {
+                        rde = fp::mac(rde, c.g[2 * t + 1], wd[r + t]);
+                        rdo = fp::mac(rdo, c.g[2 * t], wd[r + t]);
+                    }
+                    xo[2 * r] = fp::add(rae, rde);
+                    xo[2 * r + 1] = fp::add(rao, rdo);
+                }
+                T *o = out + j * ml + 8 * c0;
+                st4(o, xo[0], xo[1], xo[2], xo[3]);
+                st4(o + 4, xo[4], xo[5], xo[6], xo[7]);
             }
-            out[j * ml + 2 * u] = fp::add(rae, rde);
-            out[j * ml + 2 * u + 1] = fp::add(rao, rdo);
+        } else if (ml == 4) {
+            for (int j = threadIdx.x; j < (m >> 2); j += blockDim.x) {
+                T w[4];
+                ld4(w, in + 4 * j);                            // [a0 a1 | d0 d1]
+                const T a[2] = {w[0], w[1]}, d[2] = {w[2], w[3]};
+                T x[4];
+                tiny_syn<T, F, STRICT, 2>(a, d, x, c);
+                st4(out + 4 * j, x[0], x[1], x[2], x[3]);
+            }
+        } else if (ml == 2) {
+            for (int j = threadIdx.x; j < (m >> 1); j += blockDim.x) {
+                const T a[1] = {in[2 * j]}, d[1] = {in[2 * j + 1]};
+                T x[2];
+                tiny_syn<T, F, STRICT, 1>(a, d, x, c);
+                st2(out + 2 * j, x[0], x[1]);
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < (m >> 1); idx += blockDim.x) {
+                const int j = idx / nh, u = idx - j * nh;
+                const T *a = in + j * ml, *d = a + nh;
+                int ia = (u - (Q - 1)) % nh;
+                if (ia < 0) ia += nh;
+                T rae = fp::mul(c.h[2 * (Q - 1)], a[ia]);
+                T rao = fp::mul(c.h[2 * (Q - 1) + 1], a[ia]);
+#pragma unroll
+                for (int t = Q - 2; t >= 0; --t) {
+                    if (++ia == nh) ia = 0;
+                    rae = fp::mac(rae, c.h[2 * t], a[ia]);
+                    rao = fp::mac(rao, c.h[2 * t + 1], a[ia]);
+                }
+                int id = u;
+                T rde = fp::mul(c.g[1], d[id]);
+                T rdo = fp::mul(c.g[0], d[id]);
+#pragma unroll
+                for (int t = 1; t < Q; ++t) {
+                    if (++id == nh) id = 0;
+                    rde = fp::mac(rde, c.g[2 * t + 1], d[id]);
+                    rdo = fp::mac(rdo, c.g[2 * t], d[id]);
+                }
+                out[j * ml + 2 * u] = fp::add(rae, rde);
+                out[j * ml + 2 * u + 1] = fp::add(rao, rdo);
+            }
         }
         __syncthreads();
         T *t = in; in = out; out = t;

@@ -36,4 +36,17 @@ template <typename T>
 int32_t fused2d_tail(const PassOp<T> &op, const T *src, int64_t ld_s, int64_t bs_s, T *dst, int64_t ld_d, int64_t bs_d,
                      int nt, int levels, int64_t B, bool fw, cudaStream_t st);
 
+// ---- 2-D filter-bank levels (fir2d_f32.cu / fir2d_f64.cu): the same contract as fused2d_run, for OrthoFilter calls ----
+template <typename T> int fir2d_tile_edge(int F);
+template <typename T> bool fir2d_available();
+template <typename T>
+int32_t fir2d_run(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int64_t ll_ld, int64_t ll_bs,
+                  const ArrayGeom &g, int Lf, bool fw, void *scratch, cudaStream_t st, bool ll_to_scratch);
+// One level on B images of n x n (the fused kernels' own pointer contract).  forward: a = source (lda, bsa) -> o1 = the
+// (approx, approx) quadrant, o2 = the array whose other three quadrants are written.  inverse: a = (approx, approx)
+// quadrant source, xd = the array holding the other three quadrants -> o1 = merged n x n output.
+template <typename T>
+int32_t fir2d_level(const PassOp<T> &op, bool fw, const T *a, int64_t lda, int64_t bsa, const T *xd, int64_t ldx, int64_t bsx,
+                    T *o1, int64_t ld1, int64_t bs1, T *o2, int64_t ld2, int64_t bs2, int n, int64_t B, cudaStream_t st);
+
 } // namespace wb

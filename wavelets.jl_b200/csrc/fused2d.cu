@@ -16,115 +16,11 @@
 // Arithmetic order is the reference's (lift_inbounds!/lift_perboundary!, normalize!): in
 // STRICT mode interior elements use x + ((c0*a + c1*b)), elements whose taps wrap use ((x + c0*a) + c1*b).
 #include "fused.cuh"
+#include "tile2d_shapes.cuh"
 
 #include <cstdlib>
 
 namespace wb {
-
-// ---------------------------------------------------------------------------------------------------
-// compile-time shapes of the lifting schemes the fused kernels specialise on (coefficients stay runtime)
-// ---------------------------------------------------------------------------------------------------
-#define WB_HD __host__ __device__ static constexpr
-struct ShapeCdf97F { // U@0[2], P@1[2], U@0[2], P@1[2]      (WT.SCHEMES "cdf9/7", forward order)
-    static constexpr int N = 4;
-    WB_HD int pred(int i) { return (i & 1); }
-    WB_HD int sh(int i) { return (i & 1); }
-    WB_HD int nc(int) { return 2; }
-};
-struct ShapeCdf97I { // reversed: P@1, U@0, P@1, U@0
-    static constexpr int N = 4;
-    WB_HD int pred(int i) { return !(i & 1); }
-    WB_HD int sh(int i) { return !(i & 1); }
-    WB_HD int nc(int) { return 2; }
-};
-struct ShapeHaarF { // P@0[1], U@0[1]
-    static constexpr int N = 2;
-    WB_HD int pred(int i) { return i == 0; }
-    WB_HD int sh(int) { return 0; }
-    WB_HD int nc(int) { return 1; }
-};
-struct ShapeHaarI { // U@0, P@0
-    static constexpr int N = 2;
-    WB_HD int pred(int i) { return i == 1; }
-    WB_HD int sh(int) { return 0; }
-    WB_HD int nc(int) { return 1; }
-};
-struct ShapeDb2F { // P@0[1], U@1[2], P@-1[1]
-    static constexpr int N = 3;
-    WB_HD int pred(int i) { return i != 1; }
-    WB_HD int sh(int i) { return i == 0 ? 0 : (i == 1 ? 1 : -1); }
-    WB_HD int nc(int i) { return i == 1 ? 2 : 1; }
-};
-struct ShapeDb2I { // P@-1, U@1, P@0
-    static constexpr int N = 3;
-    WB_HD int pred(int i) { return i != 1; }
-    WB_HD int sh(int i) { return i == 0 ? -1 : (i == 1 ? 1 : 0); }
-    WB_HD int nc(int i) { return i == 1 ? 2 : 1; }
-};
-template <class S> struct Halo {
-    WB_HD int left() { int h = 0; for (int i = 0; i < S::N; ++i) h += S::sh(i) > 0 ? S::sh(i) : 0; return h; }
-    WB_HD int right() { int h = 0; for (int i = 0; i < S::N; ++i) h += (S::nc(i) - 1 - S::sh(i)) > 0 ? (S::nc(i) - 1 - S::sh(i)) : 0; return h; }
-};
-#undef WB_HD
-
-template <class S, typename T> static bool shape_matches(const LiftScheme<T> &sc) {
-    if (sc.nsteps != S::N) return false;
-    for (int i = 0; i < S::N; ++i)
-        if ((sc.is_predict[i] != 0) != (S::pred(i) != 0) || sc.shift[i] != S::sh(i) || sc.nc[i] != S::nc(i)) return false;
-    return true;
-}
-
-// coefficients of one direction, trimmed to what the fused shapes need
-template <typename T> struct LiftCoefs {
-    T c[4][2];
-    T n1, n2;
-};
-
-// ---------------------------------------------------------------------------------------------------
-// all lifting steps of one line segment, in registers.  s[p], d[p] are the polyphase pair p of the segment;
-// element 0 is global pair g0 (mod half).  Valid ranges shrink by each step's reach; the caller only consumes
-// pairs [HL, NP-HR).
-// ---------------------------------------------------------------------------------------------------
-template <typename T, class S, bool STRICT, int NP>
-__device__ __forceinline__ void lift_regs(T (&s)[NP], T (&d)[NP], const LiftCoefs<T> &lc, int g0, int half, bool edge) {
-    using fp = FP<STRICT>;
-    int lo_s = 0, hi_s = NP, lo_d = 0, hi_d = NP;
-#pragma unroll
-    for (int st = 0; st < S::N; ++st) {
-        const int sh = S::sh(st), nc = S::nc(st);
-        const bool pred = S::pred(st) != 0;
-        const int left = sh > 0 ? sh : 0, right = (nc - 1 - sh) > 0 ? (nc - 1 - sh) : 0;
-        int lo, hi;
-        if (pred) { lo = lo_s > lo_d + left ? lo_s : lo_d + left; hi = hi_s < hi_d - right ? hi_s : hi_d - right; lo_s = lo; hi_s = hi; }
-        else      { lo = lo_d > lo_s + left ? lo_d : lo_s + left; hi = hi_d < hi_s - right ? hi_d : hi_s - right; lo_d = lo; hi_d = hi; }
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            if (p >= lo && p < hi) {
-                T v = pred ? s[p] : d[p];
-                // tap indices are compile-time constants after unrolling; the clamps only silence dead-code bounds
-                const int i0 = (p - sh) < 0 ? 0 : ((p - sh) >= NP ? NP - 1 : (p - sh));
-                const int i1 = (p + 1 - sh) < 0 ? 0 : ((p + 1 - sh) >= NP ? NP - 1 : (p + 1 - sh));
-                const T t0 = pred ? d[i0] : s[i0];
-                const T t1 = (nc > 1) ? (pred ? d[i1] : s[i1]) : T(0);
-                if (nc == 1) {
-                    v = fp::mac(v, lc.c[st][0], t0);
-                } else if (STRICT) {
-                    bool interior = true;
-                    if (edge) {
-                        int gi = g0 + p;
-                        if (gi < 0) gi += half; else if (gi >= half) gi -= half;
-                        interior = (gi >= left) && (gi <= half + sh - nc);
-                    }
-                    if (interior) v = fp::add(v, fp::mac(fp::mul(lc.c[st][0], t0), lc.c[st][1], t1));
-                    else          v = fp::mac(fp::mac(v, lc.c[st][0], t0), lc.c[st][1], t1);
-                } else {
-                    v = fp::mac(fp::mac(v, lc.c[st][0], t0), lc.c[st][1], t1);
-                }
-                if (pred) s[p] = v; else d[p] = v;
-            }
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------
 // tile configuration
@@ -147,7 +43,6 @@ template <class S, int TI_, int TJ_, int SI_, int SJ_> struct Cfg2d {
     static_assert(TIp % SI == 0 && TJp % SJ == 0, "segments must tile the tile");
 };
 
-__device__ __forceinline__ int wrapi(int v, int n) { return v < 0 ? v + n : (v >= n ? v - n : v); }
 
 // one element, global -> shared, asynchronously (LDGSTS)
 template <typename T> __device__ __forceinline__ void cp_async(T *dst_smem, const T *src) {
@@ -564,10 +459,19 @@ template <typename T> static int shape_id(const LiftScheme<T> &sc, bool fw) {
 
 template <typename T>
 int fused2d_levels(const PassOp<T> &op, const ArrayGeom &g, int L, bool fw) {
-    if (!op.lifting || g.ndim != 2 || g.C != 1 || g.dim[0] != g.dim[1]) return 0;
+    if (g.ndim != 2 || g.C != 1 || g.dim[0] != g.dim[1]) return 0;
     if (env_int2("WB200_DISABLE_FUSED2D", 0)) return 0;
-    if (shape_id<T>(op.sc, fw) == 0) return 0;
     if (g.batch > 65535) return 0;
+    if (!op.lifting) {       // orthogonal filter bank: tensor-map tile kernels only (fir2d_impl.cuh); the remainder is generic
+        if (op.generic_only || env_int2("WB200_DISABLE_FIR2D", 0)) return 0;
+        const int te = fir2d_tile_edge<T>(op.fc.F);
+        int64_t n = g.dim[0];
+        if (te == 0 || n > (int64_t)1 << 30 || !fir2d_available<T>()) return 0;
+        int Lf = 0;
+        while (Lf < L && n >= te && n % te == 0) { ++Lf; n >>= 1; }
+        return Lf;
+    }
+    if (shape_id<T>(op.sc, fw) == 0) return 0;
     const int tmax = Tile2d<T>::TI > Tile2d<T>::TJ ? Tile2d<T>::TI : Tile2d<T>::TJ;
     int Lf = 0;
     int64_t n = g.dim[0];
@@ -756,6 +660,7 @@ static int32_t run2d(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int
 template <typename T>
 int32_t fused2d_run(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int64_t ll_ld, int64_t ll_bs,
                     const ArrayGeom &g, int Lf, bool fw, void *scratch, cudaStream_t st, bool ll_to_scratch) {
+    if (!op.lifting) return fir2d_run<T>(op, y, x, ll_src, ll_ld, ll_bs, g, Lf, fw, scratch, st, ll_to_scratch);
     const int id = shape_id<T>(op.sc, fw);
 #define WB_RUN(SF, SI_)                                                                                            \
     return op.strict ? run2d<T, SF, SI_, true>(op, y, x, ll_src, ll_ld, ll_bs, g, Lf, fw, scratch, st, ll_to_scratch)   \

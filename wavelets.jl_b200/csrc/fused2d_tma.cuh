@@ -427,7 +427,7 @@ template <typename T, class S, bool STRICT, class C>
 __global__ void __launch_bounds__(C::NT)
 k_lift2d_fwd_tma(const __grid_constant__ TensorMap tm_src, const T *__restrict__ src, int64_t ld_s, int64_t bs_s,
                  T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll, T *__restrict__ yd, int64_t ld_y, int64_t bs_y,
-                 int n, const __grid_constant__ LiftCoefs<T> lc) {
+                 int n, const __grid_constant__ typename CoefsOf<S, T>::type lc) {
     using fp = FP<STRICT>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -477,10 +477,10 @@ k_lift2d_fwd_tma(const __grid_constant__ TensorMap tm_src, const T *__restrict__
         __syncthreads();
         if (act) {
             const int jp0 = (j0 >> 1) - C::HL + q * C::SJ;
-            lift_regs<T, S, STRICT, C::NPJ>(s, d, lc, wrapi(jp0, nh), nh, STRICT && edge_j);
+            TileTransform<T, S, STRICT, C::NPJ>::run(s, d, lc, wrapi(jp0, nh), nh, STRICT && edge_j);
 #pragma unroll
             for (int pp = C::HL; pp < C::HL + C::SJ; ++pp) {
-                if constexpr (STRICT) {
+                if constexpr (STRICT && HasNorm<S>::value) {
                     Sm[(2 * (q * C::SJ + pp)) * C::PI + il] = fp::mul(s[pp], lc.n1);
                     Sm[(2 * (q * C::SJ + pp) + 1) * C::PI + il] = fp::mul(d[pp], lc.n2);
                 } else {                                  // fast mode: the row factor rides in the dim-1 pass below
@@ -507,18 +507,23 @@ k_lift2d_fwd_tma(const __grid_constant__ TensorMap tm_src, const T *__restrict__
         }
         __syncthreads();
         if (act) {
-            lift_regs<T, S, STRICT, C::NPI>(s, d, lc, wrapi((i0 >> 1) - C::HL + q * C::SI, nh), nh, STRICT && edge_i);
+            TileTransform<T, S, STRICT, C::NPI>::run(s, d, lc, wrapi((i0 >> 1) - C::HL + q * C::SI, nh), nh, STRICT && edge_i);
             T os[C::SI], od[C::SI];
-            T f1 = lc.n1, f2 = lc.n2;
-            if constexpr (!STRICT) {                      // fast mode: (row factor) x (column factor) in one multiply
-                const T rowf = (r & 1) ? lc.n2 : lc.n1;   // 2*HL is even: staged row parity = dim-2 parity
-                f1 = lc.n1 * rowf;
-                f2 = lc.n2 * rowf;
-            }
+            if constexpr (HasNorm<S>::value) {
+                T f1 = band_n1<S, T>(lc), f2 = band_n2<S, T>(lc);
+                if constexpr (!STRICT) {                  // fast mode: (row factor) x (column factor) in one multiply
+                    const T rowf = (r & 1) ? f2 : f1;     // 2*HL is even: staged row parity = dim-2 parity
+                    f1 = f1 * rowf;
+                    f2 = f2 * rowf;
+                }
 #pragma unroll
-            for (int pp = 0; pp < C::SI; ++pp) {
-                os[pp] = fp::mul(s[C::HL + pp], f1);
-                od[pp] = fp::mul(d[C::HL + pp], f2);
+                for (int pp = 0; pp < C::SI; ++pp) {
+                    os[pp] = fp::mul(s[C::HL + pp], f1);
+                    od[pp] = fp::mul(d[C::HL + pp], f2);
+                }
+            } else {
+#pragma unroll
+                for (int pp = 0; pp < C::SI; ++pp) { os[pp] = s[C::HL + pp]; od[pp] = d[C::HL + pp]; }
             }
             // de-interleaved: the row's s-part at [HLS, HLS + TIp), its d-part behind it (every window of this row was
             // read before the barrier above), so the store phase moves whole 16-byte pieces
@@ -577,7 +582,7 @@ template <typename T, class S, bool STRICT, class C>
 __global__ void __launch_bounds__(C::NT)
 k_lift2d_inv_tma(const __grid_constant__ TensorMap tm_ll, const __grid_constant__ TensorMap tm_x,
                  const T *__restrict__ ll, int64_t ld_ll, int64_t bs_ll, const T *__restrict__ xd, int64_t ld_x, int64_t bs_x,
-                 T *__restrict__ dst, int64_t ld_d, int64_t bs_d, int n, const __grid_constant__ LiftCoefs<T> lc) {
+                 T *__restrict__ dst, int64_t ld_d, int64_t bs_d, int n, const __grid_constant__ typename CoefsOf<S, T>::type lc) {
     using fp = FP<STRICT>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -638,18 +643,23 @@ k_lift2d_inv_tma(const __grid_constant__ TensorMap tm_ll, const __grid_constant_
             Ao = Sm + ((q / SPH) * 2 + pj) * QSZ + ql * C::PC + C::CO + (q % SPH) * 2 * C::SI;
             lds16<T, C::WINI>(ws, As);
             lds16<T, C::WINI>(wd, Ad);
+            if constexpr (HasNorm<S>::value) {
+                T f1 = band_n1<S, T>(lc), f2 = band_n2<S, T>(lc);
+                if constexpr (!STRICT) {                  // fast mode: both (reciprocal) factors of a quadrant in one multiply
+                    const T rowf = pj ? f2 : f1;
+                    f1 = f1 * rowf;
+                    f2 = f2 * rowf;
+                }
 #pragma unroll
-            T f1 = lc.n1, f2 = lc.n2;
-            if constexpr (!STRICT) {                      // fast mode: both (reciprocal) factors of a quadrant in one multiply
-                const T rowf = pj ? lc.n2 : lc.n1;
-                f1 = lc.n1 * rowf;
-                f2 = lc.n2 * rowf;
+                for (int pp = 0; pp < C::NPI; ++pp) { s[pp] = fp::mul(ws[OFF + pp], f1); d[pp] = fp::mul(wd[OFF + pp], f2); }
+            } else {
+#pragma unroll
+                for (int pp = 0; pp < C::NPI; ++pp) { s[pp] = ws[OFF + pp]; d[pp] = wd[OFF + pp]; }
             }
-            for (int pp = 0; pp < C::NPI; ++pp) { s[pp] = fp::mul(ws[OFF + pp], f1); d[pp] = fp::mul(wd[OFF + pp], f2); }
         }
         __syncthreads();
         if (act) {
-            lift_regs<T, S, STRICT, C::NPI>(s, d, lc, wrapi(ip0 - C::HL + q * C::SI, nh), nh, STRICT && edge_i);
+            TileTransform<T, S, STRICT, C::NPI>::run(s, d, lc, wrapi(ip0 - C::HL + q * C::SI, nh), nh, STRICT && edge_i);
             T o[2 * C::SI];
 #pragma unroll
             for (int pp = 0; pp < C::SI; ++pp) { o[2 * pp] = s[C::HL + pp]; o[2 * pp + 1] = d[C::HL + pp]; }
@@ -674,13 +684,13 @@ k_lift2d_inv_tma(const __grid_constant__ TensorMap tm_ll, const __grid_constant_
             A1 = Sm + (pi * 2 + 1) * QSZ + (q * C::SJ) * C::PC + c;
 #pragma unroll
             for (int pp = 0; pp < C::NPJ; ++pp) {
-                if constexpr (STRICT) { s[pp] = fp::mul(A0[pp * C::PC], lc.n1); d[pp] = fp::mul(A1[pp * C::PC], lc.n2); }
-                else                  { s[pp] = A0[pp * C::PC]; d[pp] = A1[pp * C::PC]; }      // scaled in the dim-1 pass
+                if constexpr (STRICT && HasNorm<S>::value) { s[pp] = fp::mul(A0[pp * C::PC], lc.n1); d[pp] = fp::mul(A1[pp * C::PC], lc.n2); }
+                else { s[pp] = A0[pp * C::PC]; d[pp] = A1[pp * C::PC]; }      // lifting, fast mode: scaled in the dim-1 pass
             }
         }
         __syncthreads();
         if (act) {
-            lift_regs<T, S, STRICT, C::NPJ>(s, d, lc, wrapi(jq0 - C::HL + q * C::SJ, nh), nh, STRICT && edge_j);
+            TileTransform<T, S, STRICT, C::NPJ>::run(s, d, lc, wrapi(jq0 - C::HL + q * C::SJ, nh), nh, STRICT && edge_j);
 #pragma unroll
             for (int pp = C::HL; pp < C::HL + C::SJ; ++pp) { A0[pp * C::PC] = s[pp]; A1[pp * C::PC] = d[pp]; }
         }
