@@ -576,7 +576,10 @@ def test_fastpass_wpt_full_tree(dev, mode, dtype, n, B, wname):
 # ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("wname,n,L", [("db4", 128, None), ("db4", 129, None), ("db4", 129, 4), ("haar", 37, 5),
-                                        ("sym8", 20, 4), ("db2", 5000, 7), ("coif4", 1000, 9)])
+                                        ("sym8", 20, 4), ("db2", 5000, 7), ("coif4", 1000, 9),
+                                        # fused groups: flat halo tiles, phase halo tiles, periodic phase tiles, leftovers
+                                        ("db4", 65536, 16), ("db10", 40960, 12), ("db4", 100000, 9), ("haar", 131072, 17),
+                                        ("batt2", 20000, 6)])
 def test_modwt_vs_oracle(dev, mode, dtype, wname, n, L):
     wt = wavelet(getattr(WT, wname))
     q = np.asarray(wt.qmf)

@@ -10,7 +10,7 @@ import wavelets_b200 as wb
 from wavelets_b200 import _lib
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--kind", default="filter1d", choices=["filter1d", "lift2d", "filter2d", "wpt", "filter3d"])
+ap.add_argument("--kind", default="filter1d", choices=["filter1d", "lift2d", "filter2d", "wpt", "filter3d", "modwt"])
 ap.add_argument("--dtype", default="f32")
 ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--n", type=int, default=0)
@@ -40,6 +40,12 @@ elif a.kind == "filter3d":
     x = torch.randn((n, n, n), dtype=tdt, device=dev).permute(2, 1, 0)
     for _ in range(a.reps):
         y = wb.dwt(x, wt, a.levels or 3); xr = wb.idwt(y, wt, a.levels or 3)
+elif a.kind == "modwt":
+    n = a.n or (1 << 20)
+    wt = wb.wavelet(getattr(wb.WT, a.wavelet or "db4"))
+    x = torch.randn((a.batch, n), dtype=tdt, device=dev).t()
+    for _ in range(a.reps):
+        y = wb.modwt(x, wt, a.levels or 10); xr = wb.imodwt(y, wt)
 else:
     n = a.n or (1 << 16)
     wt = wb.wavelet(getattr(wb.WT, a.wavelet or "sym8"))

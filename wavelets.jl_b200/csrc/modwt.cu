@@ -15,6 +15,8 @@
 // like `w1[t] += h[n]*v[k]` on a Vector{Float32} does; non-strict Float32 uses Float32 taps and FMA.
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
+#include <vector>
 
 namespace wb {
 
@@ -148,6 +150,263 @@ static ModwtMap make_map(int64_t n, int j, unsigned &gridx) {
     return mp;
 }
 
+// ===================================================================================================
+// fused multi-level kernels.  One launch takes K consecutive levels with the scaling coefficients resident in shared
+// memory, so a group reads V once and writes its K detail rows and one V (forward), or reads them and writes one V
+// (inverse) -- instead of a read + two writes per level.
+//   tile = (H + M) rows x 32 lanes, flat index q = 32 row + lane.  Element (row, lane) is global sample
+//   base + lane + rs (row - H)   (forward: halo rows first; inverse: owned rows first, halo after):
+//     * first group ("flat"): rs = 32 -- the tile is a contiguous run of the signal, dilation 2^i is the flat offset 2^i;
+//     * later groups ("phase", base dilation s0 = 2^j0 >= 32, n % s0 == 0): rs = s0 -- lanes are 32 consecutive phases
+//       of the stride-s0 sequences (coalesced 128-byte rows), dilation s0 2^i is the flat offset 32 * 2^i.
+//   halo mode: rows outside the owned range are recomputed per tile ((F-1)(2^K - 1) base steps of reach);
+//   periodic mode: the tile holds whole periods (a short signal, or all n/s0 positions of its phases): no halo, taps
+//   wrap inside the tile and ALL remaining levels run in the one launch.
+// Arithmetic per output is the per-level kernels' (tap order, rounding), so strict mode stays bit-identical.
+// ===================================================================================================
+struct MGroup {
+    int64_t n, rs, chunks, ntiles;
+    int j0, K, dmul, H, M, periodic, NQ;
+};
+template <int F> struct MTaps { double h[F]; double g[F]; float hf[F]; float gf[F]; };
+
+__device__ __forceinline__ int64_t gmod(int64_t g, int64_t n) {
+    if (g < 0) { g += n; if (g < 0) { g %= n; if (g < 0) g += n; } }
+    else if (g >= n) { g -= n; if (g >= n) g %= n; }
+    return g;
+}
+
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(512)
+k_modwt_group(const T *__restrict__ vin, int64_t svin, T *__restrict__ y, int64_t ys, T *__restrict__ vout, int64_t svout,
+              int64_t B, const __grid_constant__ MGroup gp, const __grid_constant__ MTaps<F> tp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int offs[F];
+    T *const buf0 = reinterpret_cast<T *>(smem_raw);
+    T *const buf1 = buf0 + ((gp.NQ + 31) & ~31);
+    const int NT = blockDim.x, tid = threadIdx.x;
+    const int64_t tile = blockIdx.x, rc = tile % gp.chunks, hi = tile / gp.chunks;
+    const int64_t base = hi * (gp.rs * gp.M) + rc * 32;
+    const int own_lo = 32 * gp.H;
+    for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+        const T *vb = vin + b * svin;
+        for (int q = tid; q < gp.NQ; q += NT) {
+            const int64_t g = base + (q & 31) + gp.rs * ((q >> 5) - gp.H);
+            buf0[q] = vb[gmod(g, gp.n)];
+        }
+        __syncthreads();
+        for (int i = 0; i < gp.K; ++i) {
+            const int d = gp.dmul << i;
+            const T *src = (i & 1) ? buf1 : buf0;
+            T *dst = (i & 1) ? buf0 : buf1;
+            if (gp.periodic) {
+                if (tid < F) offs[tid] = (int)(((int64_t)tid * d) % gp.NQ);
+                __syncthreads();
+            }
+            const int qlo = gp.periodic ? 0 : (F - 1) * ((2 << i) - 1) * gp.dmul;
+            T *wrow = y + b * ys + (int64_t)(gp.j0 + i) * gp.n;
+            for (int q = qlo + tid; q < gp.NQ; q += NT) {
+                T xs[F];
+                xs[0] = src[q];
+#pragma unroll
+                for (int k = 1; k < F; ++k) {
+                    int idx;
+                    if (gp.periodic) { idx = q - offs[k]; if (idx < 0) idx += gp.NQ; }
+                    else idx = q - k * d;
+                    xs[k] = src[idx];
+                }
+                T w, a;
+                if constexpr (sizeof(T) == 8) {
+                    w = FP<STRICT>::mul(tp.h[0], xs[0]); a = FP<STRICT>::mul(tp.g[0], xs[0]);
+#pragma unroll
+                    for (int k = 1; k < F; ++k) { w = FP<STRICT>::mac(w, tp.h[k], xs[k]); a = FP<STRICT>::mac(a, tp.g[k], xs[k]); }
+                } else if constexpr (STRICT) {
+                    w = __double2float_rn(__dmul_rn(tp.h[0], (double)xs[0])); a = __double2float_rn(__dmul_rn(tp.g[0], (double)xs[0]));
+#pragma unroll
+                    for (int k = 1; k < F; ++k) {
+                        w = __double2float_rn(__dadd_rn((double)w, __dmul_rn(tp.h[k], (double)xs[k])));
+                        a = __double2float_rn(__dadd_rn((double)a, __dmul_rn(tp.g[k], (double)xs[k])));
+                    }
+                } else {
+                    w = tp.hf[0] * xs[0]; a = tp.gf[0] * xs[0];
+#pragma unroll
+                    for (int k = 1; k < F; ++k) { w = fmaf(tp.hf[k], xs[k], w); a = fmaf(tp.gf[k], xs[k], a); }
+                }
+                dst[q] = a;
+                if (q >= own_lo) {
+                    const int64_t g = base + (q & 31) + gp.rs * ((q >> 5) - gp.H);
+                    if (g < gp.n) wrow[g] = w;
+                }
+            }
+            __syncthreads();
+        }
+        const T *fin = (gp.K & 1) ? buf1 : buf0;
+        T *vo = vout + b * svout;
+        for (int q = own_lo + tid; q < gp.NQ; q += NT) {
+            const int64_t g = base + (q & 31) + gp.rs * ((q >> 5) - gp.H);
+            if (g < gp.n) vo[g] = fin[q];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(512)
+k_imodwt_group(const T *__restrict__ vin, int64_t svin, const T *__restrict__ xw, int64_t ws, T *__restrict__ vout, int64_t svout,
+               int64_t B, const __grid_constant__ MGroup gp, const __grid_constant__ MTaps<F> tp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int offs[F];
+    const int NQP = (gp.NQ + 31) & ~31;
+    T *const buf0 = reinterpret_cast<T *>(smem_raw);
+    T *const buf1 = buf0 + NQP;
+    T *const wbuf = buf1 + NQP;
+    const int NT = blockDim.x, tid = threadIdx.x;
+    const int64_t tile = blockIdx.x, rc = tile % gp.chunks, hi = tile / gp.chunks;
+    const int64_t base = hi * (gp.rs * gp.M) + rc * 32;      // owned rows first, the halo rows behind them
+    const int own_hi = gp.periodic ? gp.NQ : 32 * gp.M;
+    for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+        const T *vb = vin + b * svin;
+        for (int q = tid; q < gp.NQ; q += NT) {
+            const int64_t g = base + (q & 31) + gp.rs * (q >> 5);
+            buf0[q] = vb[gmod(g, gp.n)];
+        }
+        int cur = 0;
+        for (int i = gp.K - 1; i >= 0; --i) {
+            const int d = gp.dmul << i;
+            const T *wcol = xw + b * ws + (int64_t)(gp.j0 + i) * gp.n;
+            const int qhi = gp.periodic ? gp.NQ : gp.NQ - (F - 1) * ((1 << gp.K) - (1 << i)) * gp.dmul;
+            const int qload = gp.periodic ? gp.NQ : qhi + (F - 1) * d;       // W_j is only read below this flat index
+            for (int q = tid; q < qload; q += NT) {
+                const int64_t g = base + (q & 31) + gp.rs * (q >> 5);
+                wbuf[q] = wcol[gmod(g, gp.n)];
+            }
+            if (gp.periodic && tid < F) offs[tid] = (int)(((int64_t)tid * d) % gp.NQ);
+            __syncthreads();
+            const T *src = cur ? buf1 : buf0;
+            T *dst = cur ? buf0 : buf1;
+            for (int q = tid; q < qhi; q += NT) {
+                T xv[F], xd[F];
+                xv[0] = src[q]; xd[0] = wbuf[q];
+#pragma unroll
+                for (int k = 1; k < F; ++k) {
+                    int idx;
+                    if (gp.periodic) { idx = q + offs[k]; if (idx >= gp.NQ) idx -= gp.NQ; }
+                    else idx = q + k * d;
+                    xv[k] = src[idx]; xd[k] = wbuf[idx];
+                }
+                T acc;
+                if constexpr (sizeof(T) == 8) {
+                    acc = FP<STRICT>::add(FP<STRICT>::mul(tp.h[0], xd[0]), FP<STRICT>::mul(tp.g[0], xv[0]));
+#pragma unroll
+                    for (int k = 1; k < F; ++k) {
+                        const double term = STRICT ? __dadd_rn(__dmul_rn(tp.h[k], xd[k]), __dmul_rn(tp.g[k], xv[k]))
+                                                   : fma(tp.g[k], (double)xv[k], tp.h[k] * (double)xd[k]);
+                        acc = FP<STRICT>::add(acc, term);
+                    }
+                } else if constexpr (STRICT) {
+                    acc = __double2float_rn(__dadd_rn(__dmul_rn(tp.h[0], (double)xd[0]), __dmul_rn(tp.g[0], (double)xv[0])));
+#pragma unroll
+                    for (int k = 1; k < F; ++k) {
+                        const double term = __dadd_rn(__dmul_rn(tp.h[k], (double)xd[k]), __dmul_rn(tp.g[k], (double)xv[k]));
+                        acc = __double2float_rn(__dadd_rn((double)acc, term));
+                    }
+                } else {
+                    acc = fmaf(tp.gf[0], xv[0], tp.hf[0] * xd[0]);
+#pragma unroll
+                    for (int k = 1; k < F; ++k) acc += fmaf(tp.gf[k], xv[k], tp.hf[k] * xd[k]);
+                }
+                dst[q] = acc;
+            }
+            __syncthreads();
+            cur ^= 1;
+        }
+        const T *fin = cur ? buf1 : buf0;
+        T *vo = vout + b * svout;
+        for (int q = tid; q < own_hi; q += NT) {
+            const int64_t g = base + (q & 31) + gp.rs * (q >> 5);
+            if (g < gp.n) vo[g] = fin[q];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host: the group plan ---------------------------------------------------------------------------
+struct MStep { bool fused; int level; MGroup g; };      // fused group, or one level (1-based) through the per-level kernel
+constexpr int MODWT_CAP_BYTES = 36864;                    // one shared-memory buffer (forward uses two, inverse three)
+
+static void plan_modwt(std::vector<MStep> &steps, int64_t n, int L, int F, int esz) {
+    steps.clear();
+    const bool can_fuse = (F >= 2 && F <= 20 && (F & 1) == 0) && std::getenv("WB200_DISABLE_MODWT_FUSED") == nullptr;
+    const int cap = MODWT_CAP_BYTES / esz, rows_cap = cap / 32;
+    int j = 0;
+    if (can_fuse) {
+        MGroup g{};
+        g.n = n; g.j0 = 0; g.rs = 32; g.dmul = 1; g.chunks = 1;
+        if (n <= cap) {
+            g.K = L; g.H = 0; g.M = (int)((n + 31) / 32); g.periodic = 1; g.NQ = (int)n; g.ntiles = 1;
+        } else {
+            int K = 0;
+            while (K < L && (int64_t)(F - 1) * ((2 << K) - 1) <= cap / 9) ++K;
+            g.K = K; g.H = ((F - 1) * ((1 << K) - 1) + 31) / 32; g.M = rows_cap - g.H; g.periodic = 0;
+            g.NQ = 32 * rows_cap; g.ntiles = (n + 32 * (int64_t)g.M - 1) / (32 * (int64_t)g.M);
+        }
+        if (g.K > 0) { steps.push_back({true, 0, g}); j = g.K; }
+    }
+    while (j < L) {
+        const int64_t s0 = (int64_t)1 << j;
+        if (!can_fuse || s0 < 32 || n % s0 != 0) { steps.push_back({false, j + 1, MGroup{}}); ++j; continue; }
+        const int64_t P = n / s0;
+        MGroup g{};
+        g.n = n; g.j0 = j; g.rs = s0; g.dmul = 32; g.chunks = s0 / 32;
+        if (P * 32 <= cap) {
+            g.K = L - j; g.H = 0; g.M = (int)P; g.periodic = 1; g.NQ = (int)P * 32; g.ntiles = g.chunks;
+        } else {
+            int K = 0;
+            while (K < L - j && (F - 1) * ((2 << K) - 1) <= rows_cap / 3) ++K;
+            if (K == 0) { steps.push_back({false, j + 1, MGroup{}}); ++j; continue; }
+            g.K = K; g.H = (F - 1) * ((1 << K) - 1); g.M = rows_cap - g.H; g.periodic = 0; g.NQ = 32 * rows_cap;
+            g.ntiles = ((n + s0 * g.M - 1) / (s0 * g.M)) * g.chunks;
+        }
+        if (g.ntiles > 0x7fffffffLL) { steps.push_back({false, j + 1, MGroup{}}); ++j; continue; }
+        steps.push_back({true, 0, g});
+        j += g.K;
+    }
+}
+
+template <int F> static void fill_mtaps(MTaps<F> &m, const ModwtTaps &tp) {
+    for (int k = 0; k < F; ++k) { m.h[k] = tp.h[k]; m.g[k] = tp.g[k]; m.hf[k] = tp.hf[k]; m.gf[k] = tp.gf[k]; }
+}
+template <typename T, int F>
+static bool launch_group(bool fw, bool strict, const MGroup &g, const T *vin, int64_t svin, T *yw, int64_t ysw, T *vout, int64_t svout,
+                         int64_t B, const ModwtTaps &tp, cudaStream_t st) {
+    MTaps<F> mt; fill_mtaps<F>(mt, tp);
+    const size_t nqp = (size_t)((g.NQ + 31) & ~31);
+    const size_t smem = (fw ? 2 : 3) * nqp * sizeof(T);
+    dim3 grid((unsigned)g.ntiles, (unsigned)(B < 65535 ? B : 65535)), block(512);
+#define WB_GO(KERN, NAME)                                                                                           \
+    {                                                                                                               \
+        auto kern = KERN;                                                                                           \
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {    \
+            (void)cudaGetLastError(); set_error("cudaFuncSetAttribute(" NAME ") failed"); return false; }            \
+        LaunchScope scope(NAME, st);                                                                                \
+        kern<<<grid, block, smem, st>>>(vin, svin, yw, ysw, vout, svout, B, g, mt);                                  \
+    }
+    if (fw) { if (strict) WB_GO((k_modwt_group<T, F, true>), "modwt_group") else WB_GO((k_modwt_group<T, F, false>), "modwt_group") }
+    else    { if (strict) WB_GO((k_imodwt_group<T, F, true>), "imodwt_group") else WB_GO((k_imodwt_group<T, F, false>), "imodwt_group") }
+#undef WB_GO
+    return check_launch(fw ? "modwt_group" : "imodwt_group");
+}
+template <typename T>
+static bool launch_group_F(bool fw, bool strict, const MGroup &g, const T *vin, int64_t svin, T *yw, int64_t ysw, T *vout, int64_t svout,
+                           int64_t B, const ModwtTaps &tp, cudaStream_t st) {
+    switch (tp.F) {
+#define WB_CASE(FF) case FF: return launch_group<T, FF>(fw, strict, g, vin, svin, yw, ysw, vout, svout, B, tp, st);
+        WB_CASE(2) WB_CASE(4) WB_CASE(6) WB_CASE(8) WB_CASE(10) WB_CASE(12) WB_CASE(14) WB_CASE(16) WB_CASE(18) WB_CASE(20)
+#undef WB_CASE
+    default: set_error("internal: fused MODWT planned for filter length %d", tp.F); return false;
+    }
+}
+
 static void make_modwt_taps(ModwtTaps &tp, const double *qmf, int flen) {
     tp.F = flen;
     const double r2 = std::sqrt(2.0);
@@ -163,21 +422,30 @@ static int maxmodwtlevels(int64_t n) { int l = 0; while (((int64_t)1 << (l + 1))
 template <typename T>
 static int32_t run_modwt(T *y, const T *x, int64_t n, int64_t B, const ModwtTaps &tp, int L, bool strict, T *scratch,
                          cudaStream_t st) {
-    // V_j lands alternately in y's last column and in the scratch so that V_L ends in y[:, L+1]
+    // every step (fused group or single level) hands V on; it lands alternately in y's last column and in the scratch so
+    // that the last step leaves V_L in y[:, L+1]
     const int64_t ys = n * (L + 1);
+    std::vector<MStep> steps;
+    plan_modwt(steps, n, L, tp.F, (int)sizeof(T));
+    const int ns = (int)steps.size();
     dim3 grid(1, (unsigned)(B < 65535 ? B : 65535)), block(256);
     const T *src = x; int64_t ssrc = n;
-    for (int j = 1; j <= L; ++j) {
-        const ModwtMap mp = make_map(n, j, grid.x);
-        const bool to_y = ((L - j) % 2 == 0);
+    for (int i = 0; i < ns; ++i) {
+        const bool to_y = ((ns - 1 - i) % 2 == 0);
         T *vdst = to_y ? (y + (int64_t)L * n) : scratch;
         const int64_t svd = to_y ? ys : n;
-        {
-            LaunchScope scope("modwt_step", st);
-            if (strict) k_modwt_step<T, true><<<grid, block, 0, st>>>(src, vdst, y + (int64_t)(j - 1) * n, n, ssrc, svd, ys, B, mp, tp);
-            else        k_modwt_step<T, false><<<grid, block, 0, st>>>(src, vdst, y + (int64_t)(j - 1) * n, n, ssrc, svd, ys, B, mp, tp);
+        if (steps[i].fused) {
+            if (!launch_group_F<T>(true, strict, steps[i].g, src, ssrc, y, ys, vdst, svd, B, tp, st)) return WB200_ECUDA;
+        } else {
+            const int j = steps[i].level;
+            const ModwtMap mp = make_map(n, j, grid.x);
+            {
+                LaunchScope scope("modwt_step", st);
+                if (strict) k_modwt_step<T, true><<<grid, block, 0, st>>>(src, vdst, y + (int64_t)(j - 1) * n, n, ssrc, svd, ys, B, mp, tp);
+                else        k_modwt_step<T, false><<<grid, block, 0, st>>>(src, vdst, y + (int64_t)(j - 1) * n, n, ssrc, svd, ys, B, mp, tp);
+            }
+            if (!check_launch("modwt_step")) return WB200_ECUDA;
         }
-        if (!check_launch("modwt_step")) return WB200_ECUDA;
         src = vdst; ssrc = svd;
     }
     return WB200_OK;
@@ -187,19 +455,27 @@ static int32_t run_imodwt(T *xo, const T *xw, int64_t n, int64_t B, const ModwtT
                           cudaStream_t st) {
     const int64_t ws = n * ncols;
     if (ncols == 1) return cudaMemcpy2DAsync(xo, n * sizeof(T), xw, ws * sizeof(T), n * sizeof(T), B, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? WB200_OK : WB200_ECUDA;
+    if (ncols - 1 > 62) { set_error("imodwt: %d columns", ncols); return WB200_EDIMS; }
+    std::vector<MStep> steps;
+    plan_modwt(steps, n, ncols - 1, tp.F, (int)sizeof(T));      // the forward plan, walked backwards
+    const int ns = (int)steps.size();
     dim3 grid(1, (unsigned)(B < 65535 ? B : 65535)), block(256);
     const T *v = xw + (int64_t)(ncols - 1) * n; int64_t sv = ws;
-    for (int j = ncols - 1; j >= 1; --j) {
-        if (j > 62) { set_error("imodwt: %d columns", ncols); return WB200_EDIMS; }
-        const ModwtMap mp = make_map(n, j, grid.x);
-        const bool to_x = ((j - 1) % 2 == 0);
+    for (int i = ns - 1; i >= 0; --i) {
+        const bool to_x = (i % 2 == 0);
         T *dst = to_x ? xo : scratch;
-        {
-            LaunchScope scope("imodwt_step", st);
-            if (strict) k_imodwt_step<T, true><<<grid, block, 0, st>>>(v, xw + (int64_t)(j - 1) * n, dst, n, sv, ws, n, B, mp, tp);
-            else        k_imodwt_step<T, false><<<grid, block, 0, st>>>(v, xw + (int64_t)(j - 1) * n, dst, n, sv, ws, n, B, mp, tp);
+        if (steps[i].fused) {
+            if (!launch_group_F<T>(false, strict, steps[i].g, v, sv, const_cast<T *>(xw), ws, dst, n, B, tp, st)) return WB200_ECUDA;
+        } else {
+            const int j = steps[i].level;
+            const ModwtMap mp = make_map(n, j, grid.x);
+            {
+                LaunchScope scope("imodwt_step", st);
+                if (strict) k_imodwt_step<T, true><<<grid, block, 0, st>>>(v, xw + (int64_t)(j - 1) * n, dst, n, sv, ws, n, B, mp, tp);
+                else        k_imodwt_step<T, false><<<grid, block, 0, st>>>(v, xw + (int64_t)(j - 1) * n, dst, n, sv, ws, n, B, mp, tp);
+            }
+            if (!check_launch("imodwt_step")) return WB200_ECUDA;
         }
-        if (!check_launch("imodwt_step")) return WB200_ECUDA;
         v = dst; sv = n;
     }
     return WB200_OK;
