@@ -21,7 +21,7 @@ def plan(n, L, F, esz):
         else:
             K = 0
             while K < L and (F - 1) * ((2 << K) - 1) <= cap // 9: K += 1
-            H = ((F - 1) * ((1 << K) - 1) + 31) // 32
+            H = ((F - 1) * ((1 << K) - 1) + 4 * K + 31) // 32
             g.update(K=K, H=H, M=rows_cap - H, periodic=0, NQ=32 * rows_cap)
             g['ntiles'] = (n + 32 * g['M'] - 1) // (32 * g['M'])
         if g['K'] > 0:
@@ -46,8 +46,9 @@ def plan(n, L, F, esz):
     return steps
 
 
-def fwd_group(g, vin, y, h, gg):
+def fwd_group(g, vin, y, h, gg, v4=False):
     n, F = g['n'], len(h)
+    lo = 0
     vout = np.full(n, np.nan)
     q = np.arange(g['NQ'])
     for tile in range(g['ntiles']):
@@ -55,10 +56,15 @@ def fwd_group(g, vin, y, h, gg):
         base = hi * g['rs'] * g['M'] + rc * 32
         gi = base + (q & 31) + g['rs'] * ((q >> 5) - g['H'])
         buf = vin[gi % n].copy()
+        lo = 0
         own = (q >= 32 * g['H']) & (gi < n)
         for i in range(g['K']):
             d = g['dmul'] << i
             qlo = 0 if g['periodic'] else (F - 1) * ((2 << i) - 1) * g['dmul']
+            if v4:      # the 128-bit kernels round every level's valid start up to a chunk
+                lo = 0 if g['periodic'] else (lo + (F - 1) * d + 3) & ~3
+                qlo = lo
+                assert qlo <= 32 * g['H'] or g['periodic']
             qq = q[qlo:]
             w = np.zeros(len(qq)); a = np.zeros(len(qq))
             for k in range(F):
@@ -78,7 +84,7 @@ def fwd_group(g, vin, y, h, gg):
     return vout
 
 
-def inv_group(g, vin, xw, h, gg):
+def inv_group(g, vin, xw, h, gg, v4=False):
     n, F = g['n'], len(h)
     vout = np.full(n, np.nan)
     q = np.arange(g['NQ'])
@@ -88,10 +94,15 @@ def inv_group(g, vin, xw, h, gg):
         gi = base + (q & 31) + g['rs'] * (q >> 5)
         buf = vin[gi % n].copy()
         own_hi = g['NQ'] if g['periodic'] else 32 * g['M']
+        hi_r = g['NQ']
         for i in range(g['K'] - 1, -1, -1):
             d = g['dmul'] << i
             qhi = g['NQ'] if g['periodic'] else g['NQ'] - (F - 1) * ((1 << g['K']) - (1 << i)) * g['dmul']
             qload = g['NQ'] if g['periodic'] else qhi + (F - 1) * d
+            if v4 and not g['periodic']:
+                hi_r = (hi_r - (F - 1) * d) & ~3
+                qhi = hi_r; qload = (qhi + (F - 1) * d + 3) & ~3
+                assert qhi >= own_hi
             assert qload <= g['NQ']
             wb = np.full(g['NQ'], np.nan); wb[:qload] = xw[gi[:qload] % n, g['j0'] + i]
             qq = q[:qhi]
@@ -111,7 +122,7 @@ def inv_group(g, vin, xw, h, gg):
     return vout
 
 
-def run(n, L, qmf, esz=4):
+def run(n, L, qmf, esz=4, v4=False):
     F = len(qmf)
     gfil = np.array(qmf[::-1]) / np.sqrt(2); hfil = np.array([(-1) ** m * qmf[m] for m in range(F)]) / np.sqrt(2)
     x = np.cumsum(np.random.default_rng(n + L).standard_normal(n))
@@ -121,7 +132,7 @@ def run(n, L, qmf, esz=4):
     v = x
     for kind, g in steps:
         if kind == 'g':
-            v = fwd_group(g, v, y, hfil, gfil)
+            v = fwd_group(g, v, y, hfil, gfil, v4)
         else:
             j = g; s = 1 << (j - 1); t = np.arange(n)
             w = np.zeros(n); a = np.zeros(n)
@@ -133,7 +144,7 @@ def run(n, L, qmf, esz=4):
     v = ref[:, L]
     for kind, g in reversed(steps):
         if kind == 'g':
-            v = inv_group(g, v, ref, hfil, gfil)
+            v = inv_group(g, v, ref, hfil, gfil, v4)
         else:
             j = g; s = 1 << (j - 1); t = np.arange(n)
             acc = np.zeros(n)
@@ -152,3 +163,6 @@ if __name__ == "__main__":
         for n, L, esz in ((129, 7, 4), (1000, 9, 8), (5000, 7, 8), (9216, 13, 4), (20000, 10, 4), (65536, 16, 4), (65536, 16, 8), (131072, 17, 4), (40960, 12, 8), (100000, 9, 4)):
             e1, e2, desc = run(n, L, qmf, esz)
             print(wn, n, L, esz, f"{e1:.2e} {e2:.2e}", desc)
+            if n % 4 == 0:
+                e1, e2, _ = run(n, L, qmf, esz, v4=True)
+                print('   v4 rounding:', f"{e1:.2e} {e2:.2e}")

@@ -304,6 +304,13 @@ __device__ __forceinline__ void tiny_syn(const T (&a)[NH], const T (&d)[NH], T (
     }
 }
 
+// Shared-memory layouts (both kernels ping-pong between two m-sample buffers):
+//   analysis input of a level  : every sub-node SPLIT into its polyphase components, all even parts first --
+//        node j (length ml, nh = ml/2): E_j at [j nh, (j+1) nh), O_j at m/2 + [j nh, (j+1) nh).  A warp's 16-byte loads are
+//        then contiguous across sub-node boundaries (per-node [E|O] storage made every small-node level 2-way conflicted:
+//        44 M bank conflicts per launch in profiles/r01c_wpt_sub_f32);
+//   synthesis input of a level : all approximation bands first -- a_j at [j nh, ..), d_j at m/2 + [j nh, ..);
+//   the last analysis level writes, and the first synthesis level reads, the natural packet order [a_j | d_j] per node.
 template <typename T, int F, bool STRICT>
 __global__ void __launch_bounds__(256)
 k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int levels, int64_t nodes,
@@ -315,24 +322,24 @@ k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *in = reinterpret_cast<T *>(smem_raw);
     T *out = in + m;
+    const int mh = m >> 1;
     const int64_t q = blockIdx.x % nodes, b = blockIdx.x / nodes;
     const int64_t base = b * n + q * (int64_t)m;
-    // split load: even samples to [0, m/2), odd samples to [m/2, m)
-    for (int p = threadIdx.x; p < (m >> 1); p += blockDim.x) {
+    for (int p = threadIdx.x; p < mh; p += blockDim.x) {      // split load of the root node
         in[p] = S[base + 2 * p];
-        in[(m >> 1) + p] = S[base + 2 * p + 1];
+        in[mh + p] = S[base + 2 * p + 1];
     }
     __syncthreads();
     for (int l = 0; l < levels; ++l) {
         const int ml = m >> l, nh = ml >> 1;
         const bool last = (l == levels - 1);
-        const bool split_out = !last && (nh % 2 == 0);       // the next level wants its sub-nodes split (needs an even length)
-        // (an odd nh can only be followed by no level at all: m % 2^levels == 0)
+        const int hh = nh >> 1;                               // half length of a child (the next level's nh)
+        // child cidx (2j: approximation, 2j+1: detail) of the next level: E' at cidx*hh, O' at mh + cidx*hh
         if (nh >= 4 && (nh & 3) == 0) {
-            const int cpn = nh >> 2;                          // chunks per half sub-node
+            const int cpn = nh >> 2;                          // 16-byte chunks per component of a sub-node
             for (int idx = threadIdx.x; idx < (m >> 3); idx += blockDim.x) {
                 const int j = idx / cpn, c0 = idx - j * cpn;
-                const T *E = in + j * ml, *O = E + nh;
+                const T *E = in + j * nh, *O = E + mh;
                 T we[4 * NCH], wo[4 * NCH];
                 int ci = c0 - CL;
                 ci %= cpn; if (ci < 0) ci += cpn;
@@ -357,38 +364,36 @@ k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
                     for (int t = 1; t < F; ++t) qd = fp::mac(qd, c.g[F - 1 - t], (t & 1) ? wo[4 * CL + r + 1 - Q + (t - 1) / 2] : we[4 * CL + r + 1 - Q + t / 2]);
                     dv[r] = qd;
                 }
-                T *oa = out + j * ml, *od = oa + nh;
                 const int k0 = 4 * c0;
-                if (split_out) {
-                    const int hh = nh >> 1;
-                    st2(oa + (k0 >> 1), av[0], av[2]); st2(oa + hh + (k0 >> 1), av[1], av[3]);
-                    st2(od + (k0 >> 1), dv[0], dv[2]); st2(od + hh + (k0 >> 1), dv[1], dv[3]);
+                if (!last) {
+                    T *ea = out + (2 * j) * hh + (k0 >> 1), *ed = out + (2 * j + 1) * hh + (k0 >> 1);
+                    st2(ea, av[0], av[2]); st2(ea + mh, av[1], av[3]);
+                    st2(ed, dv[0], dv[2]); st2(ed + mh, dv[1], dv[3]);
                 } else {
-                    st4(oa + k0, av[0], av[1], av[2], av[3]);
-                    st4(od + k0, dv[0], dv[1], dv[2], dv[3]);
+                    st4(out + j * ml + k0, av[0], av[1], av[2], av[3]);
+                    st4(out + j * ml + nh + k0, dv[0], dv[1], dv[2], dv[3]);
                 }
             }
         } else if (ml == 4) {
             for (int j = threadIdx.x; j < (m >> 2); j += blockDim.x) {
-                T w[4];
-                ld4(w, in + 4 * j);                            // [E0 E1 | O0 O1]
-                const T xe[2] = {w[0], w[1]}, xo[2] = {w[2], w[3]};
+                const T xe[2] = {in[2 * j], in[2 * j + 1]}, xo[2] = {in[mh + 2 * j], in[mh + 2 * j + 1]};
                 T a[2], d[2];
                 tiny_ana<T, F, STRICT, 4>(xe, xo, a, d, c);
-                st4(out + 4 * j, a[0], a[1], d[0], d[1]);      // children of 2 samples: split == natural
+                if (!last) { st2(out + 2 * j, a[0], d[0]); st2(out + mh + 2 * j, a[1], d[1]); }   // children 2j, 2j+1 of one sample pair each
+                else st4(out + 4 * j, a[0], a[1], d[0], d[1]);
             }
-        } else if (ml == 2) {
-            for (int j = threadIdx.x; j < (m >> 1); j += blockDim.x) {
-                const T xe[1] = {in[2 * j]}, xo[1] = {in[2 * j + 1]};
+        } else if (ml == 2) {                                 // (always the last level)
+            for (int j = threadIdx.x; j < mh; j += blockDim.x) {
+                const T xe[1] = {in[j]}, xo[1] = {in[mh + j]};
                 T a[1], d[1];
                 tiny_ana<T, F, STRICT, 2>(xe, xo, a, d, c);
                 st2(out + 2 * j, a[0], d[0]);
             }
         } else {
             // any other sub-node length: one pair per thread, modular walk through the split components
-            for (int idx = threadIdx.x; idx < (m >> 1); idx += blockDim.x) {
+            for (int idx = threadIdx.x; idx < mh; idx += blockDim.x) {
                 const int j = idx / nh, k = idx - j * nh;
-                const T *E = in + j * ml, *O = E + nh;
+                const T *E = in + j * nh, *O = E + mh;
                 int ia = 2 * k;
                 T a = fp::mul(c.h[0], E[ia >> 1]);
 #pragma unroll
@@ -404,14 +409,12 @@ k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
                     if (++id == ml) id = 0;
                     d = fp::mac(d, c.g[F - 1 - t], (id & 1) ? O[id >> 1] : E[id >> 1]);
                 }
-                T *oa = out + j * ml, *od = oa + nh;
-                if (split_out) {
-                    const int hh = nh >> 1;
-                    oa[(k & 1) * hh + (k >> 1)] = a;
-                    od[(k & 1) * hh + (k >> 1)] = d;
+                if (!last) {            // (nh is even here: another level follows)
+                    out[(k & 1) * mh + (2 * j) * hh + (k >> 1)] = a;
+                    out[(k & 1) * mh + (2 * j + 1) * hh + (k >> 1)] = d;
                 } else {
-                    oa[k] = a;
-                    od[k] = d;
+                    out[j * ml + k] = a;
+                    out[j * ml + nh + k] = d;
                 }
             }
         }
@@ -431,18 +434,25 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *in = reinterpret_cast<T *>(smem_raw);
     T *out = in + m;
+    const int mh = m >> 1;
     const int64_t q = blockIdx.x % nodes, b = blockIdx.x / nodes;
     const int64_t base = b * n + q * (int64_t)m;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) in[i] = S[base + i];
+    {   // natural packet order -> band-split: node j of the deepest level: a_j to [j nh), d_j to mh + [j nh)
+        const int ml = m >> (levels - 1), nh = ml >> 1;
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            const int j = i / ml, r = i - j * ml;
+            in[(r < nh ? 0 : mh - nh) + j * nh + r] = S[base + i];
+        }
+    }
     __syncthreads();
     for (int l = levels - 1; l >= 0; --l) {
         const int ml = m >> l, nh = ml >> 1;
+        // node j's output (ml samples) is band (j & 1) of its parent j >> 1 for the next, shallower level
         if (nh >= 4 && (nh & 3) == 0) {
-            // four output pairs per thread: a[u0-Q+1 .. u0+3] and d[u0 .. u0+2+Q] in registers (16-byte chunks, chunk wrap)
             const int cpn = nh >> 2;
             for (int idx = threadIdx.x; idx < (m >> 3); idx += blockDim.x) {
                 const int j = idx / cpn, c0 = idx - j * cpn;
-                const T *A = in + j * ml, *Dd = A + nh;
+                const T *A = in + j * nh, *Dd = A + mh;
                 T wa[4 * (CL + 1)], wd[4 * (CL + 1)];
                 int ci = c0 - CL;
                 ci %= cpn; if (ci < 0) ci += cpn;
@@ -464,7 +474,6 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
                 T xo[8];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    // a[u - t] = wa[4 CL + r - t]; d[u + t] = wd[r + t]
                     T rae = fp::mul(c.h[2 * (Q - 1)], wa[4 * CL + r - (Q - 1)]);
                     T rao = fp::mul(c.h[2 * (Q - 1) + 1], wa[4 * CL + r - (Q - 1)]);
 #pragma unroll
@@ -482,30 +491,28 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
                     xo[2 * r] = fp::add(rae, rde);
                     xo[2 * r + 1] = fp::add(rao, rdo);
                 }
-                T *o = out + j * ml + 8 * c0;
+                T *o = out + (j & 1) * mh + (j >> 1) * ml + 8 * c0;
                 st4(o, xo[0], xo[1], xo[2], xo[3]);
                 st4(o + 4, xo[4], xo[5], xo[6], xo[7]);
             }
         } else if (ml == 4) {
             for (int j = threadIdx.x; j < (m >> 2); j += blockDim.x) {
-                T w[4];
-                ld4(w, in + 4 * j);                            // [a0 a1 | d0 d1]
-                const T a[2] = {w[0], w[1]}, d[2] = {w[2], w[3]};
+                const T a[2] = {in[2 * j], in[2 * j + 1]}, d[2] = {in[mh + 2 * j], in[mh + 2 * j + 1]};
                 T x[4];
                 tiny_syn<T, F, STRICT, 2>(a, d, x, c);
-                st4(out + 4 * j, x[0], x[1], x[2], x[3]);
+                st4(out + (j & 1) * mh + (j >> 1) * 4, x[0], x[1], x[2], x[3]);
             }
         } else if (ml == 2) {
-            for (int j = threadIdx.x; j < (m >> 1); j += blockDim.x) {
-                const T a[1] = {in[2 * j]}, d[1] = {in[2 * j + 1]};
+            for (int j = threadIdx.x; j < mh; j += blockDim.x) {
+                const T a[1] = {in[j]}, d[1] = {in[mh + j]};
                 T x[2];
                 tiny_syn<T, F, STRICT, 1>(a, d, x, c);
-                st2(out + 2 * j, x[0], x[1]);
+                st2(out + (j & 1) * mh + (j >> 1) * 2, x[0], x[1]);
             }
         } else {
-            for (int idx = threadIdx.x; idx < (m >> 1); idx += blockDim.x) {
+            for (int idx = threadIdx.x; idx < mh; idx += blockDim.x) {
                 const int j = idx / nh, u = idx - j * nh;
-                const T *a = in + j * ml, *d = a + nh;
+                const T *a = in + j * nh, *d = a + mh;
                 int ia = (u - (Q - 1)) % nh;
                 if (ia < 0) ia += nh;
                 T rae = fp::mul(c.h[2 * (Q - 1)], a[ia]);
@@ -525,8 +532,9 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
                     rde = fp::mac(rde, c.g[2 * t + 1], d[id]);
                     rdo = fp::mac(rdo, c.g[2 * t], d[id]);
                 }
-                out[j * ml + 2 * u] = fp::add(rae, rde);
-                out[j * ml + 2 * u + 1] = fp::add(rao, rdo);
+                T *o = out + (j & 1) * mh + (j >> 1) * ml;
+                o[2 * u] = fp::add(rae, rde);
+                o[2 * u + 1] = fp::add(rao, rdo);
             }
         }
         __syncthreads();

@@ -330,6 +330,249 @@ k_imodwt_group(const T *__restrict__ vin, int64_t svin, const T *__restrict__ xw
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// 128-bit editions of the two group kernels (n % 4 == 0, 16-byte aligned arrays): every loop moves FOUR consecutive
+// flat elements.  The scalar kernels above issue one LDS per tap per output and were instruction-bound (82 % issue-slot
+// utilisation, profiles/r01c_modwt_f32); here a tap of dilation d >= 4 is one 16-byte shared-memory load for four
+// outputs, and the two finest dilations (1, 2) read one register window of 16-byte chunks.  Valid ranges are rounded to
+// chunk boundaries per level (the flat plan reserves 4 K extra halo elements for that).
+// ---------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void v_ld4(T (&w)[4], const T *p) {
+    if constexpr (sizeof(T) == 4) { const float4 q = *reinterpret_cast<const float4 *>(p); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
+    else { const double2 q0 = *reinterpret_cast<const double2 *>(p), q1 = *reinterpret_cast<const double2 *>(p + 2); w[0] = q0.x; w[1] = q0.y; w[2] = q1.x; w[3] = q1.y; }
+}
+template <typename T> __device__ __forceinline__ void v_st4(T *p, const T (&w)[4]) {
+    if constexpr (sizeof(T) == 4) *reinterpret_cast<float4 *>(p) = make_float4(w[0], w[1], w[2], w[3]);
+    else { *reinterpret_cast<double2 *>(p) = make_double2(w[0], w[1]); *reinterpret_cast<double2 *>(p + 2) = make_double2(w[2], w[3]); }
+}
+// one forward tap on four outputs (the per-level kernels' arithmetic)
+template <typename T, int F, bool STRICT>
+__device__ __forceinline__ void fwd_tap(T (&w)[4], T (&a)[4], const T (&x)[4], const MTaps<F> &tp, int k, bool first) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if constexpr (sizeof(T) == 8) {
+            if (first) { w[r] = FP<STRICT>::mul(tp.h[k], x[r]); a[r] = FP<STRICT>::mul(tp.g[k], x[r]); }
+            else       { w[r] = FP<STRICT>::mac(w[r], tp.h[k], x[r]); a[r] = FP<STRICT>::mac(a[r], tp.g[k], x[r]); }
+        } else if constexpr (STRICT) {
+            if (first) { w[r] = __double2float_rn(__dmul_rn(tp.h[k], (double)x[r])); a[r] = __double2float_rn(__dmul_rn(tp.g[k], (double)x[r])); }
+            else {
+                w[r] = __double2float_rn(__dadd_rn((double)w[r], __dmul_rn(tp.h[k], (double)x[r])));
+                a[r] = __double2float_rn(__dadd_rn((double)a[r], __dmul_rn(tp.g[k], (double)x[r])));
+            }
+        } else {
+            if (first) { w[r] = tp.hf[k] * x[r]; a[r] = tp.gf[k] * x[r]; }
+            else       { w[r] = fmaf(tp.hf[k], x[r], w[r]); a[r] = fmaf(tp.gf[k], x[r], a[r]); }
+        }
+    }
+}
+// one inverse tap: acc (+)= h[k] w + g[k] v
+template <typename T, int F, bool STRICT>
+__device__ __forceinline__ void inv_tap(T (&acc)[4], const T (&xw_)[4], const T (&xv)[4], const MTaps<F> &tp, int k, bool first) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if constexpr (sizeof(T) == 8) {
+            if (first) acc[r] = FP<STRICT>::add(FP<STRICT>::mul(tp.h[k], xw_[r]), FP<STRICT>::mul(tp.g[k], xv[r]));
+            else {
+                const double term = STRICT ? __dadd_rn(__dmul_rn(tp.h[k], xw_[r]), __dmul_rn(tp.g[k], xv[r]))
+                                           : fma(tp.g[k], (double)xv[r], tp.h[k] * (double)xw_[r]);
+                acc[r] = FP<STRICT>::add(acc[r], term);
+            }
+        } else if constexpr (STRICT) {
+            const double term = __dadd_rn(__dmul_rn(tp.h[k], (double)xw_[r]), __dmul_rn(tp.g[k], (double)xv[r]));
+            if (first) acc[r] = __double2float_rn(term);
+            else       acc[r] = __double2float_rn(__dadd_rn((double)acc[r], term));
+        } else {
+            if (first) acc[r] = fmaf(tp.gf[k], xv[r], tp.hf[k] * xw_[r]);
+            else       acc[r] += fmaf(tp.gf[k], xv[r], tp.hf[k] * xw_[r]);
+        }
+    }
+}
+
+template <typename T, int F, bool STRICT, int D>      // the two finest dilations of a flat group: register window
+__device__ __forceinline__ void fwd_window(T (&w)[4], T (&a)[4], const T *src, int c, int NCq, bool periodic, const MTaps<F> &tp) {
+    constexpr int NCW = ((F - 1) * D + 3) / 4 + 1;
+    T win[4 * NCW];
+    int ci = c - (NCW - 1);
+    if (periodic) { ci %= NCq; if (ci < 0) ci += NCq; }
+#pragma unroll
+    for (int i = 0; i < NCW; ++i) {
+        T t4[4];
+        v_ld4(t4, src + 4 * ci);
+        win[4 * i] = t4[0]; win[4 * i + 1] = t4[1]; win[4 * i + 2] = t4[2]; win[4 * i + 3] = t4[3];
+        ++ci;
+        if (periodic && ci == NCq) ci = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < F; ++k) {
+        const T x[4] = {win[4 * (NCW - 1) + 0 - k * D], win[4 * (NCW - 1) + 1 - k * D], win[4 * (NCW - 1) + 2 - k * D], win[4 * (NCW - 1) + 3 - k * D]};
+        fwd_tap<T, F, STRICT>(w, a, x, tp, k, k == 0);
+    }
+}
+template <typename T, int F, bool STRICT, int D>
+__device__ __forceinline__ void inv_window(T (&acc)[4], const T *src, const T *wsrc, int c, int NCq, bool periodic, const MTaps<F> &tp) {
+    constexpr int NCW = ((F - 1) * D + 3) / 4 + 1;
+    T wv[4 * NCW], ww[4 * NCW];
+    int ci = c;
+#pragma unroll
+    for (int i = 0; i < NCW; ++i) {
+        T t4[4];
+        v_ld4(t4, src + 4 * ci);
+        wv[4 * i] = t4[0]; wv[4 * i + 1] = t4[1]; wv[4 * i + 2] = t4[2]; wv[4 * i + 3] = t4[3];
+        v_ld4(t4, wsrc + 4 * ci);
+        ww[4 * i] = t4[0]; ww[4 * i + 1] = t4[1]; ww[4 * i + 2] = t4[2]; ww[4 * i + 3] = t4[3];
+        ++ci;
+        if (periodic && ci == NCq) ci = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < F; ++k) {
+        const T xv[4] = {wv[k * D], wv[k * D + 1], wv[k * D + 2], wv[k * D + 3]};
+        const T xd[4] = {ww[k * D], ww[k * D + 1], ww[k * D + 2], ww[k * D + 3]};
+        inv_tap<T, F, STRICT>(acc, xd, xv, tp, k, k == 0);
+    }
+}
+
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(512)
+k_modwt_group_v4(const T *__restrict__ vin, int64_t svin, T *__restrict__ y, int64_t ys, T *__restrict__ vout, int64_t svout,
+                 int64_t B, const __grid_constant__ MGroup gp, const __grid_constant__ MTaps<F> tp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int offs[F];
+    T *const buf0 = reinterpret_cast<T *>(smem_raw);
+    T *const buf1 = buf0 + ((gp.NQ + 31) & ~31);
+    const int NT = blockDim.x, tid = threadIdx.x;
+    const int NCq = gp.NQ >> 2;
+    const int64_t tile = blockIdx.x, rc = tile % gp.chunks, hi = tile / gp.chunks;
+    const int64_t base = hi * (gp.rs * gp.M) + rc * 32;
+    const int own_c = 8 * gp.H;                              // first owned chunk
+    for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+        const T *vb = vin + b * svin;
+        for (int c = tid; c < NCq; c += NT) {
+            const int q = 4 * c;
+            const int64_t g = gmod(base + (q & 31) + gp.rs * ((q >> 5) - gp.H), gp.n);     // chunk-aligned, never straddles n
+            T t4[4];
+            v_ld4(t4, vb + g);
+            v_st4(buf0 + q, t4);
+        }
+        __syncthreads();
+        int lo = 0;
+        for (int i = 0; i < gp.K; ++i) {
+            const int d = gp.dmul << i;
+            const T *src = (i & 1) ? buf1 : buf0;
+            T *dst = (i & 1) ? buf0 : buf1;
+            if (gp.periodic) {
+                if (tid < F) offs[tid] = (int)(((int64_t)tid * d) % gp.NQ);
+                __syncthreads();
+            } else lo = (lo + (F - 1) * d + 3) & ~3;
+            T *wrow = y + b * ys + (int64_t)(gp.j0 + i) * gp.n;
+            for (int c = (lo >> 2) + tid; c < NCq; c += NT) {
+                const int q = 4 * c;
+                T w[4], a[4];
+                if (d == 1) fwd_window<T, F, STRICT, 1>(w, a, src, c, NCq, gp.periodic != 0, tp);
+                else if (d == 2) fwd_window<T, F, STRICT, 2>(w, a, src, c, NCq, gp.periodic != 0, tp);
+                else {
+#pragma unroll
+                    for (int k = 0; k < F; ++k) {
+                        int idx;
+                        if (gp.periodic) { idx = q - offs[k]; if (idx < 0) idx += gp.NQ; }
+                        else idx = q - k * d;
+                        T x[4];
+                        v_ld4(x, src + idx);
+                        fwd_tap<T, F, STRICT>(w, a, x, tp, k, k == 0);
+                    }
+                }
+                v_st4(dst + q, a);
+                if (c >= own_c) {
+                    const int64_t g = base + (q & 31) + gp.rs * ((q >> 5) - gp.H);
+                    if (g < gp.n) v_st4(wrow + g, w);
+                }
+            }
+            __syncthreads();
+        }
+        const T *fin = (gp.K & 1) ? buf1 : buf0;
+        T *vo = vout + b * svout;
+        for (int c = own_c + tid; c < NCq; c += NT) {
+            const int q = 4 * c;
+            const int64_t g = base + (q & 31) + gp.rs * ((q >> 5) - gp.H);
+            if (g < gp.n) { T t4[4]; v_ld4(t4, fin + q); v_st4(vo + g, t4); }
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int F, bool STRICT>
+__global__ void __launch_bounds__(512)
+k_imodwt_group_v4(const T *__restrict__ vin, int64_t svin, const T *__restrict__ xw, int64_t ws, T *__restrict__ vout, int64_t svout,
+                  int64_t B, const __grid_constant__ MGroup gp, const __grid_constant__ MTaps<F> tp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int offs[F];
+    const int NQP = (gp.NQ + 31) & ~31;
+    T *const buf0 = reinterpret_cast<T *>(smem_raw);
+    T *const buf1 = buf0 + NQP;
+    T *const wbuf = buf1 + NQP;
+    const int NT = blockDim.x, tid = threadIdx.x;
+    const int NCq = gp.NQ >> 2;
+    const int64_t tile = blockIdx.x, rc = tile % gp.chunks, hi = tile / gp.chunks;
+    const int64_t base = hi * (gp.rs * gp.M) + rc * 32;
+    const int own_c = gp.periodic ? NCq : 8 * gp.M;          // owned chunks: [0, own_c)
+    for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
+        const T *vb = vin + b * svin;
+        for (int c = tid; c < NCq; c += NT) {
+            const int q = 4 * c;
+            const int64_t g = gmod(base + (q & 31) + gp.rs * (q >> 5), gp.n);
+            T t4[4];
+            v_ld4(t4, vb + g);
+            v_st4(buf0 + q, t4);
+        }
+        int cur = 0, qhi = gp.NQ;
+        for (int i = gp.K - 1; i >= 0; --i) {
+            const int d = gp.dmul << i;
+            const T *wcol = xw + b * ws + (int64_t)(gp.j0 + i) * gp.n;
+            int qload = gp.NQ;
+            if (!gp.periodic) { qhi = (qhi - (F - 1) * d) & ~3; qload = (qhi + (F - 1) * d + 3) & ~3; }
+            for (int c = tid; c < (qload >> 2); c += NT) {
+                const int q = 4 * c;
+                const int64_t g = gmod(base + (q & 31) + gp.rs * (q >> 5), gp.n);
+                T t4[4];
+                v_ld4(t4, wcol + g);
+                v_st4(wbuf + q, t4);
+            }
+            if (gp.periodic && tid < F) offs[tid] = (int)(((int64_t)tid * d) % gp.NQ);
+            __syncthreads();
+            const T *src = cur ? buf1 : buf0;
+            T *dst = cur ? buf0 : buf1;
+            for (int c = tid; c < (qhi >> 2); c += NT) {
+                const int q = 4 * c;
+                T acc[4];
+                if (d == 1) inv_window<T, F, STRICT, 1>(acc, src, wbuf, c, NCq, gp.periodic != 0, tp);
+                else if (d == 2) inv_window<T, F, STRICT, 2>(acc, src, wbuf, c, NCq, gp.periodic != 0, tp);
+                else {
+#pragma unroll
+                    for (int k = 0; k < F; ++k) {
+                        int idx;
+                        if (gp.periodic) { idx = q + offs[k]; if (idx >= gp.NQ) idx -= gp.NQ; }
+                        else idx = q + k * d;
+                        T xv[4], xd[4];
+                        v_ld4(xv, src + idx);
+                        v_ld4(xd, wbuf + idx);
+                        inv_tap<T, F, STRICT>(acc, xd, xv, tp, k, k == 0);
+                    }
+                }
+                v_st4(dst + q, acc);
+            }
+            __syncthreads();
+            cur ^= 1;
+        }
+        const T *fin = cur ? buf1 : buf0;
+        T *vo = vout + b * svout;
+        for (int c = tid; c < own_c; c += NT) {
+            const int q = 4 * c;
+            const int64_t g = base + (q & 31) + gp.rs * (q >> 5);
+            if (g < gp.n) { T t4[4]; v_ld4(t4, fin + q); v_st4(vo + g, t4); }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- host: the group plan ---------------------------------------------------------------------------
 struct MStep { bool fused; int level; MGroup g; };      // fused group, or one level (1-based) through the per-level kernel
 constexpr int MODWT_CAP_BYTES = 36864;                    // one shared-memory buffer (forward uses two, inverse three)
@@ -347,7 +590,7 @@ static void plan_modwt(std::vector<MStep> &steps, int64_t n, int L, int F, int e
         } else {
             int K = 0;
             while (K < L && (int64_t)(F - 1) * ((2 << K) - 1) <= cap / 9) ++K;
-            g.K = K; g.H = ((F - 1) * ((1 << K) - 1) + 31) / 32; g.M = rows_cap - g.H; g.periodic = 0;
+            g.K = K; g.H = ((F - 1) * ((1 << K) - 1) + 4 * K + 31) / 32; g.M = rows_cap - g.H; g.periodic = 0;   // (+4K: chunk rounding of the 128-bit kernels)
             g.NQ = 32 * rows_cap; g.ntiles = (n + 32 * (int64_t)g.M - 1) / (32 * (int64_t)g.M);
         }
         if (g.K > 0) { steps.push_back({true, 0, g}); j = g.K; }
@@ -391,8 +634,18 @@ static bool launch_group(bool fw, bool strict, const MGroup &g, const T *vin, in
         LaunchScope scope(NAME, st);                                                                                \
         kern<<<grid, block, smem, st>>>(vin, svin, yw, ysw, vout, svout, B, g, mt);                                  \
     }
-    if (fw) { if (strict) WB_GO((k_modwt_group<T, F, true>), "modwt_group") else WB_GO((k_modwt_group<T, F, false>), "modwt_group") }
-    else    { if (strict) WB_GO((k_imodwt_group<T, F, true>), "imodwt_group") else WB_GO((k_imodwt_group<T, F, false>), "imodwt_group") }
+    auto al = [](const void *q, int64_t stride) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (stride & 3) == 0; };
+    // (Float64 keeps the scalar kernels: four doubles per thread are two 16-byte accesses 32 bytes apart across lanes --
+    //  2-way bank conflicts -- and measured 1.7x slower than one double per lane)
+    const bool v4 = sizeof(T) == 4 && (g.n & 3) == 0 && (g.NQ & 3) == 0 && al(vin, svin) && al(yw, ysw) && al(vout, svout) &&
+                    std::getenv("WB200_MODWT_SCALAR") == nullptr;
+    if (v4) {
+        if (fw) { if (strict) WB_GO((k_modwt_group_v4<T, F, true>), "modwt_group") else WB_GO((k_modwt_group_v4<T, F, false>), "modwt_group") }
+        else    { if (strict) WB_GO((k_imodwt_group_v4<T, F, true>), "imodwt_group") else WB_GO((k_imodwt_group_v4<T, F, false>), "imodwt_group") }
+    } else {
+        if (fw) { if (strict) WB_GO((k_modwt_group<T, F, true>), "modwt_group") else WB_GO((k_modwt_group<T, F, false>), "modwt_group") }
+        else    { if (strict) WB_GO((k_imodwt_group<T, F, true>), "imodwt_group") else WB_GO((k_imodwt_group<T, F, false>), "imodwt_group") }
+    }
 #undef WB_GO
     return check_launch(fw ? "modwt_group" : "imodwt_group");
 }
