@@ -9,6 +9,7 @@
 #include "tile2d_shapes.cuh"
 #include "fused2d_tma.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace wb {
@@ -17,17 +18,18 @@ namespace wb {
 // resident CTAs per SM
 template <typename T, int F> struct FirTile {
     static constexpr bool SMALL = (sizeof(T) == 8) || (F >= 14);
-    static constexpr int TI = 128, TJ = SMALL ? 32 : 64, SI = SMALL ? 8 : 16, SJ = SMALL ? 8 : 16;
+    // Float32 filters of 10 and 12 taps are built in both configurations (WB200_FIR_SMALL = 0 / 1 overrides the default)
+    static constexpr bool BOTH = (sizeof(T) == 4) && (F == 10 || F == 12);
 };
-template <typename T, int F, bool FW>
-using FirCfg = Cfg3<T, std::conditional_t<FW, ShapeFirA<F>, ShapeFirS<F>>, FirTile<T, F>::TI, FirTile<T, F>::TJ, FirTile<T, F>::SI, FirTile<T, F>::SJ>;
+template <typename T, int F, bool FW, bool SMALL>
+using FirCfg = Cfg3<T, std::conditional_t<FW, ShapeFirA<F>, ShapeFirS<F>>, 128, SMALL ? 32 : 64, SMALL ? 8 : 16, SMALL ? 8 : 16>;
 
-template <typename T, int F, bool STRICT, bool FW>
-static int32_t fir_launch_level(const T *a, int64_t lda, int64_t bsa, const T *xd, int64_t ldx, int64_t bsx,
-                                T *o1, int64_t ld1, int64_t bs1, T *o2, int64_t ld2, int64_t bs2,
-                                int n, int64_t B, const FirCoefs<T, F> &fc, cudaStream_t st) {
+template <typename T, int F, bool STRICT, bool FW, bool SMALL>
+static int32_t fir_launch_cfg(const T *a, int64_t lda, int64_t bsa, const T *xd, int64_t ldx, int64_t bsx,
+                              T *o1, int64_t ld1, int64_t bs1, T *o2, int64_t ld2, int64_t bs2,
+                              int n, int64_t B, const FirCoefs<T, F> &fc, cudaStream_t st) {
     using S = std::conditional_t<FW, ShapeFirA<F>, ShapeFirS<F>>;
-    using C3 = FirCfg<T, F, FW>;
+    using C3 = FirCfg<T, F, FW, SMALL>;
     const int nx = n / C3::TI, ny = n / C3::TJ;
     if constexpr (FW) {
         TensorMap tm;
@@ -57,6 +59,20 @@ static int32_t fir_launch_level(const T *a, int64_t lda, int64_t bsa, const T *x
             kern<<<dim3((unsigned)nx, (unsigned)ny, (unsigned)B), C3::NT, smem, st>>>(tml, tmx, a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, n, fc);
         }
         return check_launch("fused_fir2d_inv") ? WB200_OK : WB200_ECUDA;
+    }
+}
+
+template <typename T, int F, bool STRICT, bool FW>
+static int32_t fir_launch_level(const T *a, int64_t lda, int64_t bsa, const T *xd, int64_t ldx, int64_t bsx,
+                                T *o1, int64_t ld1, int64_t bs1, T *o2, int64_t ld2, int64_t bs2,
+                                int n, int64_t B, const FirCoefs<T, F> &fc, cudaStream_t st) {
+    if constexpr (FirTile<T, F>::BOTH) {
+        const char *e = std::getenv("WB200_FIR_SMALL");
+        const bool small = e ? (std::atoi(e) != 0) : FirTile<T, F>::SMALL;
+        if (small) return fir_launch_cfg<T, F, STRICT, FW, true>(a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, o2, ld2, bs2, n, B, fc, st);
+        return fir_launch_cfg<T, F, STRICT, FW, false>(a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, o2, ld2, bs2, n, B, fc, st);
+    } else {
+        return fir_launch_cfg<T, F, STRICT, FW, FirTile<T, F>::SMALL>(a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, o2, ld2, bs2, n, B, fc, st);
     }
 }
 

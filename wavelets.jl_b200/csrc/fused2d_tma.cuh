@@ -449,13 +449,30 @@ k_lift2d_fwd_tma(const __grid_constant__ TensorMap tm_src, const T *__restrict__
     const bool edge_i = (blockIdx.x == 0) || (blockIdx.x == gridDim.x - 1);
     const bool edge_j = (blockIdx.y == 0) || (blockIdx.y == gridDim.y - 1);
     if (edge_i || edge_j) {
+        // only the four halo strips can hold zero-filled cells: walk those (a 512^2 plane has 62 % border tiles, and a
+        // sweep over the whole tile doubled their instruction count -- profiles/r01d_fir3d_db6_f32.md)
         const T *sb = src + (int64_t)b * bs_s;
         constexpr int WI = C::HLS + C::TI + 2 * C::HR;
-        for (int idx = tid; idx < C::RJ * WI; idx += C::NT) {
-            const int r = idx / WI, il = idx - r * WI;
+        auto patch = [&](int r, int il) {
             const int gi = iorg + il, gj = jorg + r;
             if (gi < 0 || gi >= n || gj < 0 || gj >= n)
                 Sm[r * C::PI + il] = sb[(int64_t)wrapi(gj, n) * ld_s + wrapi(gi, n)];
+        };
+        if (blockIdx.x == 0) {
+            if constexpr (C::HLS > 0)
+                for (int idx = tid; idx < C::RJ * C::HLS; idx += C::NT) patch(idx / C::HLS, idx % C::HLS);
+        }
+        if (blockIdx.x == gridDim.x - 1) {
+            if constexpr (C::HR > 0)
+                for (int idx = tid; idx < C::RJ * 2 * C::HR; idx += C::NT) patch(idx / (2 * C::HR), C::HLS + C::TI + idx % (2 * C::HR));
+        }
+        if (blockIdx.y == 0) {
+            if constexpr (C::HL > 0)
+                for (int idx = tid; idx < 2 * C::HL * WI; idx += C::NT) patch(idx / WI, idx % WI);
+        }
+        if (blockIdx.y == gridDim.y - 1) {
+            if constexpr (C::HR > 0)
+                for (int idx = tid; idx < 2 * C::HR * WI; idx += C::NT) patch(2 * C::HL + C::TJ + idx / WI, idx % WI);
         }
         __syncthreads();
     }
@@ -606,13 +623,10 @@ k_lift2d_inv_tma(const __grid_constant__ TensorMap tm_ll, const __grid_constant_
     mb_wait(bar, 0);
     const bool edge_i = (blockIdx.x == 0) || (blockIdx.x == gridDim.x - 1);
     const bool edge_j = (blockIdx.y == 0) || (blockIdx.y == gridDim.y - 1);
-    if (edge_i || edge_j) {   // quadrant-relative wrap of the halo cells
+    if (edge_i || edge_j) {   // quadrant-relative wrap of the halo cells: the four halo strips of each quadrant array
         const T *llb = ll + (int64_t)b * bs_ll;
         const T *xb = xd + (int64_t)b * bs_x;
-        for (int idx = tid; idx < 4 * C::JQ * C::IW; idx += C::NT) {
-            const int c = idx % C::IW;
-            const int rest = idx / C::IW;
-            const int ql = rest % C::JQ, quad = rest / C::JQ;
+        auto patch = [&](int quad, int ql, int c) {
             const int gc = corg + c, gq = qorg + ql;
             if (gc < 0 || gc >= nh || gq < 0 || gq >= nh) {
                 const int wc = wrapi(gc, nh), wq = wrapi(gq, nh);
@@ -620,6 +634,22 @@ k_lift2d_inv_tma(const __grid_constant__ TensorMap tm_ll, const __grid_constant_
                 Sm[quad * QSZ + ql * C::PC + c] = (quad == 0) ? llb[(int64_t)wq * ld_ll + wc]
                                                               : xb[(int64_t)(pj * nh + wq) * ld_x + pi * nh + wc];
             }
+        };
+        if (blockIdx.x == 0) {
+            if constexpr (C::CO > 0)
+                for (int idx = tid; idx < 4 * C::JQ * C::CO; idx += C::NT) patch(idx / (C::JQ * C::CO), (idx / C::CO) % C::JQ, idx % C::CO);
+        }
+        if (blockIdx.x == gridDim.x - 1) {
+            if constexpr (C::HR > 0)
+                for (int idx = tid; idx < 4 * C::JQ * C::HR; idx += C::NT) patch(idx / (C::JQ * C::HR), (idx / C::HR) % C::JQ, C::CO + C::TIp + idx % C::HR);
+        }
+        if (blockIdx.y == 0) {
+            if constexpr (C::HL > 0)
+                for (int idx = tid; idx < 4 * C::HL * C::IW; idx += C::NT) patch(idx / (C::HL * C::IW), (idx / C::IW) % C::HL, idx % C::IW);
+        }
+        if (blockIdx.y == gridDim.y - 1) {
+            if constexpr (C::HR > 0)
+                for (int idx = tid; idx < 4 * C::HR * C::IW; idx += C::NT) patch(idx / (C::HR * C::IW), C::HL + C::TJp + (idx / C::IW) % C::HR, idx % C::IW);
         }
         __syncthreads();
     }

@@ -575,12 +575,21 @@ k_imodwt_group_v4(const T *__restrict__ vin, int64_t svin, const T *__restrict__
 
 // ---- host: the group plan ---------------------------------------------------------------------------
 struct MStep { bool fused; int level; MGroup g; };      // fused group, or one level (1-based) through the per-level kernel
-constexpr int MODWT_CAP_BYTES = 36864;                    // one shared-memory buffer (forward uses two, inverse three)
+constexpr int MODWT_CAP_BYTES = 36864;                    // one shared-memory buffer of a forward tile (two per CTA)
+constexpr int MODWT_INV_CAP_BYTES = 24576;                // inverse: three per CTA; the smaller tile keeps 3 CTAs per SM resident, which
+                                                          // hides the per-level W loads better (L = 10: 2.23 -> 1.95 ms; sweep in DESIGN.md)
 
-static void plan_modwt(std::vector<MStep> &steps, int64_t n, int L, int F, int esz) {
+static int modwt_cap_bytes(bool fw) {      // shared-memory bytes of one tile buffer (tuning knob; the plan adapts to it)
+    const char *e = std::getenv(fw ? "WB200_MODWT_CAP" : "WB200_MODWT_INV_CAP");
+    int v = e ? std::atoi(e) : (fw ? MODWT_CAP_BYTES : MODWT_INV_CAP_BYTES);
+    if (v < 8192) v = 8192;
+    if (v > (fw ? 110 : 72) * 1024) v = (fw ? 110 : 72) * 1024;
+    return v & ~1023;
+}
+static void plan_modwt(std::vector<MStep> &steps, int64_t n, int L, int F, int esz, bool fw) {
     steps.clear();
     const bool can_fuse = (F >= 2 && F <= 20 && (F & 1) == 0) && std::getenv("WB200_DISABLE_MODWT_FUSED") == nullptr;
-    const int cap = MODWT_CAP_BYTES / esz, rows_cap = cap / 32;
+    const int cap = modwt_cap_bytes(fw) / esz, rows_cap = cap / 32;
     int j = 0;
     if (can_fuse) {
         MGroup g{};
@@ -679,7 +688,7 @@ static int32_t run_modwt(T *y, const T *x, int64_t n, int64_t B, const ModwtTaps
     // that the last step leaves V_L in y[:, L+1]
     const int64_t ys = n * (L + 1);
     std::vector<MStep> steps;
-    plan_modwt(steps, n, L, tp.F, (int)sizeof(T));
+    plan_modwt(steps, n, L, tp.F, (int)sizeof(T), true);
     const int ns = (int)steps.size();
     dim3 grid(1, (unsigned)(B < 65535 ? B : 65535)), block(256);
     const T *src = x; int64_t ssrc = n;
@@ -710,7 +719,7 @@ static int32_t run_imodwt(T *xo, const T *xw, int64_t n, int64_t B, const ModwtT
     if (ncols == 1) return cudaMemcpy2DAsync(xo, n * sizeof(T), xw, ws * sizeof(T), n * sizeof(T), B, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? WB200_OK : WB200_ECUDA;
     if (ncols - 1 > 62) { set_error("imodwt: %d columns", ncols); return WB200_EDIMS; }
     std::vector<MStep> steps;
-    plan_modwt(steps, n, ncols - 1, tp.F, (int)sizeof(T));      // the forward plan, walked backwards
+    plan_modwt(steps, n, ncols - 1, tp.F, (int)sizeof(T), false);      // a plan of its own (three buffers per tile), walked backwards
     const int ns = (int)steps.size();
     dim3 grid(1, (unsigned)(B < 65535 ? B : 65535)), block(256);
     const T *v = xw + (int64_t)(ncols - 1) * n; int64_t sv = ws;
