@@ -52,50 +52,102 @@ def parse():
 # clocks sampler (B200_PROFILING.md "clocks line")
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread (10 ms period; started before the
+    warm-up so that it is already running when the timed steps begin, samples outside [mark_begin, mark_end] are dropped),
+    `nvidia-smi -lms` as the fallback when NVML is not importable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+            0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nv = index, [], None, None
+        self.samples, self.stop_flag, self.t0, self.t1, self.smax = [], False, None, None, None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nv = (pynvml, h)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        pynvml, h = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                try:
+                    bits = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    bits = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.samples.append((time.perf_counter(), mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def _inside(self, t):
+        return (self.t0 is None or t >= self.t0) and (self.t1 is None or t <= self.t1)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
+        self.stop_flag = True
+        sm, smax, reasons = [], self.smax, set()
+        if self.nv is not None:
+            for t, mhz, bits in self.samples:
+                if not self._inside(t):
+                    continue
+                sm.append(mhz)
+                for bit, nm in self.BITS.items():
+                    if bits & bit:
+                        reasons.add(nm)
+            src = "nvml"
+        elif self.proc:
+            self.proc.terminate()
             try:
-                sm.append(float(f[0])); smax = float(f[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for t, r in self.rows:
+                f = [x.strip() for x in r.split(",")]
+                if len(f) < 7 or not self._inside(t):
+                    continue
+                try:
+                    sm.append(float(f[0])); smax = float(f[1])
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            src = "nvidia-smi"
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source (NVML and nvidia-smi unavailable)"], "samples": 0}
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": src}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -226,21 +278,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
     L.wb200_launch_count(1)
     L.wb200_profile_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark_begin()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     L.wb200_profile_enable(0)
     ms_total = e0.elapsed_time(e1)
     launches = int(L.wb200_launch_count(1))
