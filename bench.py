@@ -480,6 +480,17 @@ def run_extras(L, wb, _lib, dev, stream, args):
     res["modwt_db4_1048576_f32_L10"] = {"msamples_per_s_pair": nm * Bm / (ms * 1e-3) / 1e6, "ms_per_pair": ms, "achieved_gbs_pair": gbs,
                                         "frac_of_hbm_peak": gbs / peak, "signals": Bm,
                                         "note": "bytes = 2 (L + 2) n B sizeof(T): the transform is (L + 1)-fold redundant"}
+    del xm
+    # denoise = noisest (level-1 dwt + device MAD) -> dwt -> threshold -> idwt, one 1-D signal of 2^24
+    # samples, sym5, L = 6, hard VisuShrink, no cycle spinning; a pure enqueue (the noise level never visits the host).
+    # Compulsory bytes: read x + write y.
+    nd_ = 1 << 24
+    xd = torch.randn(nd_, dtype=torch.float32, device=dev)
+    ms = timed_pair(lambda: wb.denoise(xd), lambda y: y)
+    gbs = 2.0 * nd_ * 4 / (ms * 1e-3) / 1e9
+    res["denoise_sym5_16777216_f32_L6"] = {"msamples_per_s": nd_ / (ms * 1e-3) / 1e6, "ms_per_call": ms, "ms_per_pair": ms,
+                                           "achieved_gbs_pair": gbs, "frac_of_hbm_peak": gbs / peak,
+                                           "note": "bytes = 2 n sizeof(T) (read x, write y); the pipeline itself makes four passes"}
     return res
 
 

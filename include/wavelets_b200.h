@@ -122,6 +122,30 @@ int32_t wb200_imodwt(void *x, const void *xw, int64_t n, int64_t batch, const do
                      int32_t dtype, void *workspace, size_t workspace_bytes, void *stream, uint32_t flags);
 int32_t wb200_maxmodwttransformlevels(int64_t n);                             /* non_dyadic.jl:24-25 */
 
+/* ---- thresholding and denoising: the main caller of the transforms, device end to end ----
+ * threshold!(x, TH, t)            src/Threshold/threshold_main.jl:35-117 (BiggestTH is not on the device path yet)
+ * noisest(x, wt)                  src/Threshold/denoising.jl:88-106: level-1 transform, MAD of y[n1/2+1 : n1] (linear
+ *                                 indices: the second half of the FIRST column, whatever ndim) over 0.6745.  Returns the
+ *                                 number, so it waits for the stream.
+ * denoise(x, wt; L, dnt, TI, nspin)  denoising.jl:22-82, dnt = VisuShrink(th_kind, tfac): t = sigma * tfac.  Pure enqueue:
+ *                                 sigma = NaN estimates the noise level on the device (noisest) and the threshold kernel
+ *                                 reads it from device memory; a finite sigma is the caller's `estnoise` result.
+ * wkind 0: wt = nothing, 1: OrthoFilter (qmf, flen), 2: GLS (steps, nsteps, norm1, norm2).  One array per call. */
+#define WB200_TH_HARD 0
+#define WB200_TH_SOFT 1
+#define WB200_TH_SEMISOFT 2
+#define WB200_TH_STEIN 3
+#define WB200_TH_NEG 4
+#define WB200_TH_POS 5
+int32_t wb200_threshold(void *x, int64_t count, int32_t kind, double t, int32_t dtype, void *stream);
+int32_t wb200_noisest(double *sigma_out, const void *x, int32_t ndim, const int64_t *dims, int32_t wkind,
+                      const double *qmf, int32_t flen, const wb200_lift_step *steps, int32_t nsteps, double norm1,
+                      double norm2, int32_t dtype, void *stream, uint32_t flags);
+int32_t wb200_denoise(void *y, const void *x, int32_t ndim, const int64_t *dims, int32_t wkind, const double *qmf,
+                      int32_t flen, const wb200_lift_step *steps, int32_t nsteps, double norm1, double norm2, int32_t L,
+                      int32_t th_kind, double tfac, double sigma, int32_t TI, const int32_t *nspin, int32_t dtype,
+                      void *stream, uint32_t flags);
+
 /* ---- host-buffer forms (end-to-end path): x_host / y_host are HOST pointers (pinned memory gives full
  * PCIe bandwidth).  The batch is cut into chunks that are copied in, transformed and copied out on
  * alternating streams so the three stages overlap; the call returns after the last chunk has landed

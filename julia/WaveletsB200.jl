@@ -122,6 +122,42 @@ function Wavelets.imodwt(xw::CuMatrix{T}, wt::OrthoFilter) where {T<:Union{Float
     check(rc); x
 end
 
+# ---- Threshold: threshold!, noisest, denoise on the device (src/Threshold/threshold_main.jl, denoising.jl) ---------------
+th_code(::Wavelets.Threshold.HardTH) = Int32(0);     th_code(::Wavelets.Threshold.SoftTH) = Int32(1)
+th_code(::Wavelets.Threshold.SemiSoftTH) = Int32(2); th_code(::Wavelets.Threshold.SteinTH) = Int32(3)
+th_code(::Wavelets.Threshold.NegTH) = Int32(4);      th_code(::Wavelets.Threshold.PosTH) = Int32(5)
+function Wavelets.Threshold.threshold!(x::CuArray{T}, TH::Wavelets.Threshold.THType, t::Real=0) where {T<:Union{Float32,Float64}}
+    rc = ccall((:wb200_threshold, LIB), Int32, (CuPtr{Cvoid}, Int64, Int32, Float64, Int32, Ptr{Cvoid}),
+               pointer(x), length(x), th_code(TH), Float64(t), dtype_code(T), CUDA.stream().handle)
+    check(rc); x
+end
+# wkind / qmf / steps of a wavelet (nothing, OrthoFilter, GLS)
+wt_args(::Nothing) = (Int32(0), Float64[], LiftStep[], 0.0, 0.0)
+wt_args(f::OrthoFilter) = (Int32(1), Vector{Float64}(f.qmf), LiftStep[], 0.0, 0.0)
+wt_args(s::GLS) = (Int32(2), Float64[], LiftStep.(s.step), s.norm1, s.norm2)
+function Wavelets.Threshold.noisest(x::CuArray{T,N}, wt::Union{DiscreteWavelet,Nothing}=Wavelets.Threshold.DEFAULT_WAVELET) where {T<:Union{Float32,Float64},N}
+    wk, qmf, steps, n1, n2 = wt_args(wt); out = Ref{Float64}(0)
+    rc = ccall((:wb200_noisest, LIB), Int32,
+               (Ptr{Float64}, CuPtr{Cvoid}, Int32, Ptr{Int64}, Int32, Ptr{Float64}, Int32, Ptr{LiftStep}, Int32, Float64, Float64, Int32, Ptr{Cvoid}, UInt32),
+               out, pointer(x), N, dims3(x), wk, qmf, length(qmf), steps, length(steps), n1, n2, dtype_code(T), CUDA.stream().handle, flags())
+    check(rc); out[]
+end
+function Wavelets.Threshold.denoise(x::CuArray{T,N}, wt::Union{DiscreteWavelet,Nothing}=Wavelets.Threshold.DEFAULT_WAVELET;
+                                    L::Int=min(maxtransformlevels(x), 6), dnt::Wavelets.Threshold.VisuShrink=Wavelets.Threshold.VisuShrink(size(x, 1)),
+                                    estnoise::Union{Function,Nothing}=nothing, TI::Bool=false,
+                                    nspin::Union{Int,Tuple}=ntuple(_ -> 8, N)) where {T<:Union{Float32,Float64},N}
+    wk, qmf, steps, n1, n2 = wt_args(wt)
+    sigma = estnoise === nothing ? NaN : Float64(estnoise(x, wt))       # NaN: noisest on the device, no host round trip
+    spin = Int32[nspin..., ones(Int32, 3 - length(nspin))...]
+    y = similar(x)
+    rc = ccall((:wb200_denoise, LIB), Int32,
+               (CuPtr{Cvoid}, CuPtr{Cvoid}, Int32, Ptr{Int64}, Int32, Ptr{Float64}, Int32, Ptr{LiftStep}, Int32, Float64, Float64, Int32,
+                Int32, Float64, Float64, Int32, Ptr{Int32}, Int32, Ptr{Cvoid}, UInt32),
+               pointer(y), pointer(x), N, dims3(x), wk, qmf, length(qmf), steps, length(steps), n1, n2, L,
+               th_code(dnt.th), dnt.t, sigma, TI, spin, dtype_code(T), CUDA.stream().handle, flags())
+    check(rc); y
+end
+
 # ---- column-wise batch forms (the last dimension indexes independent signals / images) ---------------------------
 export dwtc, idwtc
 dwtc(x::CuArray, wt::OrthoFilter, L::Integer=minimum(maxtransformlevels.(size(x)[1:end-1]))) =

@@ -213,3 +213,56 @@ def imodwt(xw, qmf):
                                              C.c_int(ncols), q.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(len(q)))
     _check(rc)
     return x
+
+
+# ---- Threshold / denoising ------------------------------------------------------------------
+TH_KINDS = {"hard": 0, "soft": 1, "semisoft": 2, "stein": 3, "neg": 4, "pos": 5}
+
+
+def _wt_args(wt):
+    """wt: None | object with .qmf (OrthoFilter) | object with .step/.norm1/.norm2 (GLS) -> ctypes argument tuple"""
+    null_d = C.POINTER(C.c_double)()
+    if wt is None:
+        return 0, null_d, 0, None, 0, 0.0, 0.0, ()
+    if hasattr(wt, "qmf"):
+        q = np.ascontiguousarray(wt.qmf, dtype=np.float64)
+        return 1, q.ctypes.data_as(C.POINTER(C.c_double)), len(q), None, 0, 0.0, 0.0, (q,)
+    st = make_steps(wt.step)
+    return 2, null_d, 0, st, len(st), float(wt.norm1), float(wt.norm2), (st,)
+
+
+def threshold(x, kind, t=0.0):
+    """Reference `threshold(x, TH, t)`; kind in TH_KINDS."""
+    y = _fcopy(x)
+    sfx, ct = _sfx(y.dtype)
+    getattr(lib(), "orc_threshold" + sfx)(y.ctypes.data_as(C.c_void_p), C.c_int64(y.size), C.c_int(TH_KINDS[kind]), C.c_double(float(t)))
+    return y
+
+
+def noisest(x, wt):
+    x = _fcopy(x)
+    sfx, ct = _sfx(x.dtype)
+    wk, qp, fl, st, ns, n1, n2, keep = _wt_args(wt)
+    sig = C.c_double(0.0)
+    rc = getattr(lib(), "orc_noisest" + sfx)(C.byref(sig), x.ctypes.data_as(C.c_void_p), C.c_int(x.ndim), _dims(x.shape), C.c_int(wk),
+                                             qp, C.c_int(fl), st, C.c_int(ns), C.c_double(n1), C.c_double(n2))
+    _check(rc)
+    return sig.value
+
+
+def denoise(x, wt, L, kind="hard", tfac=None, sigma=None, TI=False, nspin=8):
+    """Reference `denoise(x, wt; L, dnt=VisuShrink(th, tfac), TI, nspin)`; sigma=None -> noisest."""
+    x = _fcopy(x)
+    sfx, ct = _sfx(x.dtype)
+    if tfac is None:
+        tfac = float(np.sqrt(2 * np.log(x.shape[0])))
+    wk, qp, fl, st, ns, n1, n2, keep = _wt_args(wt)
+    sp = [nspin] * x.ndim if isinstance(nspin, int) and x.ndim == 1 else ([nspin] + [1] * (x.ndim - 1) if isinstance(nspin, int) else list(nspin))
+    spin = (C.c_int32 * 3)(*(sp + [1] * (3 - len(sp))))
+    y = np.empty_like(x, order="F")
+    rc = getattr(lib(), "orc_denoise" + sfx)(y.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), C.c_int(x.ndim), _dims(x.shape),
+                                             C.c_int(wk), qp, C.c_int(fl), st, C.c_int(ns), C.c_double(n1), C.c_double(n2), C.c_int(int(L)),
+                                             C.c_int(TH_KINDS[kind]), C.c_double(float(tfac)),
+                                             C.c_double(float("nan") if sigma is None else float(sigma)), C.c_int(1 if TI else 0), spin)
+    _check(rc)
+    return y

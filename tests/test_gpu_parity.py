@@ -702,3 +702,112 @@ def test_fused_fir3d_vs_oracle(dev, mode, dtype, wname):
     yb = wb.dwtc(to_gpu(xb, dev), wt, 2)
     check(yb, orc.dwt_filter_batch(xb, 3, wt.qmf, 2), mode, 6, 8.0)
     check(wb.idwtc(yb, wt, 2), orc.dwt_filter_batch(to_np(yb), 3, wt.qmf, 2, fw=False), mode, 6, 8.0)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Threshold / noisest / denoise (src/Threshold/threshold_main.jl, denoising.jl)
+# ------------------------------------------------------------------------------------------------------
+def _doppler(n):
+    t = np.linspace(0, 1, n)
+    return np.sqrt(t * (1 - t)) * np.sin(2 * np.pi * 1.05 / (t + 0.05))
+
+
+TH = {"hard": wb.HardTH, "soft": wb.SoftTH, "semisoft": wb.SemiSoftTH, "stein": wb.SteinTH, "neg": wb.NegTH, "pos": wb.PosTH}
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind", ["hard", "soft", "semisoft", "stein", "neg", "pos"])
+def test_threshold_vs_oracle(dev, dtype, kind):
+    x = (rng(11).standard_normal(5000) * 2).astype(dtype)
+    x[:4] = [0.0, -0.0, 2.0, -2.0]                                 # the boundary cases abs(x) == t and signed zeros
+    args = () if kind in ("neg", "pos") else (2.0,)
+    y = wb.threshold(to_gpu(x, dev), TH[kind](), *args)
+    assert np.array_equal(to_np(y), orc.threshold(x, kind, 2.0), equal_nan=True)
+    x2 = to_gpu(x.reshape(50, 100), dev)
+    assert wb.threshold_(x2, TH[kind](), *args) is x2
+    assert np.array_equal(to_np(x2), orc.threshold(x.reshape(50, 100), kind, 2.0), equal_nan=True)
+    with pytest.raises(NotImplementedError):
+        wb.threshold(to_gpu(x, dev), wb.BiggestTH(), 3)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_noisest_vs_oracle(dev, mode, dtype):
+    wf, wl = wavelet(WT.sym5), wavelet(WT.cdf97, WT.Lifting)
+    for shape in ((256,), (1000,), (4096,), (32, 32), (16, 16, 16), (1 << 17,)):
+        x = (_doppler(shape[0]).reshape((-1,) + (1,) * (len(shape) - 1)) + 0.1 * rng(sum(shape)).standard_normal(shape)).astype(dtype)
+        for wt in (wf, wl, None):
+            ref = orc.noisest(x, wt)
+            got = wb.noisest(to_gpu(x, dev), wt)
+            if mode == "strict" or wt is None:
+                assert got == ref, (shape, wt, got, ref)
+            else:
+                assert abs(got - ref) <= (1e-5 if dtype == np.float32 else 1e-12) * max(1.0, abs(ref))
+    # odd lengths exist only without a transform; round(Int, n/2 + 1) rounds ties to even
+    for n in (5, 7, 9, 11, 1001):
+        x = rng(n).standard_normal(n).astype(dtype)
+        assert wb.noisest(to_gpu(x, dev), None) == orc.noisest(x, None)
+    # exact order statistics at scale, against an independent sort on the device
+    xb = torch.randn(1 << 22, device=dev, dtype=torch.float64 if dtype == np.float64 else torch.float32)
+    v = xb[(1 << 21):].clone()
+    s = torch.sort(v).values
+    m = v.numel()
+    med = s[m // 2 - 1] / 2 + s[m // 2] / 2
+    s2 = torch.sort((v - med).abs()).values
+    mad = s2[m // 2 - 1] / 2 + s2[m // 2] / 2
+    assert wb.noisest(xb, None) == float(mad) / 0.6745          # (host division: torch divides by multiplying with the reciprocal)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind", ["hard", "soft", "semisoft", "stein"])
+def test_denoise_vs_oracle(dev, mode, dtype, kind):
+    wf, wl = wavelet(WT.sym5), wavelet(WT.cdf97, WT.Lifting)
+    cases = [((256,), wf, False, None), ((256,), wf, True, None), ((1024,), wl, True, 5), ((256,), None, False, None),
+             ((32, 32), wf, True, (3, 2)), ((64, 64), wl, False, None), ((16, 16, 16), wf, True, (2, 2, 2)), ((256, 256), wf, False, None)]
+    for shape, wt, TI, nspin in cases:
+        n = shape[0]
+        x = (_doppler(n).reshape((-1,) + (1,) * (len(shape) - 1)) + 0.1 * rng(n + len(shape)).standard_normal(shape)).astype(dtype)
+        L = min(wb.maxtransformlevels(n), 6)
+        kw = {} if nspin is None else {"nspin": nspin}
+        ref = orc.denoise(x, wt, L, kind=kind, TI=TI, **({"nspin": nspin} if nspin is not None else ({"nspin": 8} if len(shape) == 1 else {"nspin": tuple(8 for _ in shape)})))
+        got = to_np(wb.denoise(to_gpu(x, dev), wt, L=L, dnt=wb.VisuShrink(TH[kind](), np.sqrt(2 * np.log(n))), TI=TI, **kw))
+        assert got.shape == ref.shape and got.dtype == ref.dtype
+        if mode == "strict":
+            assert np.array_equal(got, ref), (shape, wt, TI, float(np.max(np.abs(got - ref))))
+        else:
+            # FMA contraction moves coefficients by ulps; one that sits on the threshold may flip: allow rare outliers
+            d = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+            tol = 1e-4 if dtype == np.float32 else 1e-10
+            assert np.mean(d > tol) <= 0.01 and np.median(d) <= tol, (shape, wt, TI, float(d.max()))
+        # a caller-supplied noise level (estnoise) gives the same result as the estimate it replaces
+    x = (_doppler(512) + 0.1 * rng(3).standard_normal(512)).astype(dtype)
+    sig = orc.noisest(x, wf)
+    a = wb.denoise(to_gpu(x, dev), wf, estnoise=lambda xx, ww: sig, dnt=wb.VisuShrink(TH[kind](), 3.0))
+    b = orc.denoise(x, wf, 6, kind=kind, tfac=3.0, sigma=sig)
+    if mode == "strict":
+        assert np.array_equal(to_np(a), b)
+
+
+def test_denoise_defaults_errors_and_scale(dev):
+    n = 256
+    x0 = _doppler(n)
+    x = x0 + 0.05 * rng(6).standard_normal(n)
+    xg = to_gpu(x, dev)
+    for kw in ({"TI": True}, {"TI": True, "nspin": 8}, {"TI": False}):      # the reference's own smoke calls (test/threshold.jl:17-21)
+        y = to_np(wb.denoise(xg, **kw))
+        assert np.linalg.norm(y - x0) < np.linalg.norm(x - x0)
+    assert to_np(wb.denoise(xg, None)).shape == (n,)
+    assert tuple(wb.denoise(to_gpu(rng(1).standard_normal((32, 32)), dev), TI=True).shape) == (32, 32)
+    with pytest.raises(wb.ArgumentError, match="square/cube"):
+        wb.denoise(to_gpu(rng(1).standard_normal((16, 32)), dev))
+    with pytest.raises(RuntimeError, match="TI not supported"):
+        wb.denoise(xg, None, TI=True)
+    with pytest.raises(NotImplementedError):
+        wb.denoise(xg, dnt=wb.VisuShrink(wb.BiggestTH(), 1.0))
+    # N = 2^20, Float32: the noise level is recovered and cycle-spun denoising removes most of the noise
+    N = 1 << 20
+    t = torch.linspace(0, 1, N, device=dev, dtype=torch.float64)
+    clean = (torch.sqrt(t * (1 - t)) * torch.sin(2 * np.pi * 1.05 / (t + 0.05))).float()
+    noisy = clean + 0.05 * torch.randn(N, device=dev)
+    assert abs(wb.noisest(noisy) - 0.05) < 2e-3
+    den = wb.denoise(noisy, TI=True, nspin=4)
+    assert float((den - clean).norm()) < 0.25 * float((noisy - clean).norm())

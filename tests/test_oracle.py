@@ -221,3 +221,77 @@ def test_modwt_float32():
     assert W.dtype == np.float32
     assert np.allclose(orc.imodwt(W, q), x, rtol=0, atol=2e-6)
     assert np.allclose(W, orc.modwt(x.astype(np.float64), q, 3), rtol=0, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Threshold / denoise.  The reference's tests assert nothing about these values
+# (test/threshold.jl: "TODO @test something"): the definitions are checked against an independent numpy statement,
+# denoise against the properties its construction implies.
+# ------------------------------------------------------------------------------------------------------
+def _np_threshold(x, kind, t):
+    x = x.astype(np.float64)
+    if kind == "hard":
+        return np.where(np.abs(x) <= t, 0.0, x)
+    if kind == "soft":
+        return np.where(np.abs(x) - t < 0, 0.0, np.sign(x) * (np.abs(x) - t))
+    if kind == "semisoft":
+        sh = np.abs(x) - t
+        y = np.where(sh < 0, 0.0, np.where(sh - t < 0, np.sign(x) * sh * 2, x))
+        return np.where(x <= 2 * t, y, x)
+    if kind == "stein":
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sh = 1 - t * t / (x * x)
+        return np.where(sh < 0, 0.0, x * sh)
+    if kind == "neg":
+        return np.where(x < 0, 0.0, x)
+    return np.where(x > 0, 0.0, x)
+
+
+@pytest.mark.parametrize("kind", ["hard", "soft", "semisoft", "stein", "neg", "pos"])
+def test_threshold_definitions(kind):
+    x = rng(5).standard_normal(200) * 2                           # the reference's own smoke input (test/threshold.jl:3)
+    assert np.allclose(orc.threshold(x, kind, 2.0), _np_threshold(x, kind, 2.0), rtol=0, atol=1e-15)
+    x32 = x.astype(np.float32)
+    y32 = orc.threshold(x32, kind, 2.0)
+    assert y32.dtype == np.float32 and np.allclose(y32, _np_threshold(x32, kind, 2.0), rtol=0, atol=1e-6)
+
+
+def _doppler(n):
+    t = np.linspace(0, 1, n)
+    return np.sqrt(t * (1 - t)) * np.sin(2 * np.pi * 1.05 / (t + 0.05))
+
+
+def test_noisest_and_denoise_properties():
+    n = 256
+    x0 = _doppler(n)
+    x = x0 + 0.05 * rng(6).standard_normal(n)
+    wt = wavelet(WT.sym5)
+    sig = orc.noisest(x, wt)
+    assert 0.03 < sig < 0.08                                      # true noise level 0.05
+    # MAD by hand on the level-1 detail coefficients
+    d = orc.dwt_filter(x, wt.qmf, 1)[n // 2:]
+    mad = np.median(np.abs(d - np.median(d)))
+    assert abs(sig - mad / 0.6745) <= 1e-15
+    # wt = nothing: plain thresholding of x at sigma * sqrt(2 log n), sigma from x's own second half
+    xs = x[n // 2:]
+    sig0 = np.median(np.abs(xs - np.median(xs))) / 0.6745
+    assert abs(orc.noisest(x, None) - sig0) <= 1e-15
+    assert np.array_equal(orc.denoise(x, None, 0), orc.threshold(x, "hard", sig0 * np.sqrt(2 * np.log(n))))
+    # not TI = dwt -> threshold -> idwt; TI with one spin is the same thing
+    y = orc.denoise(x, wt, 6)
+    c = orc.threshold(orc.dwt_filter(x, wt.qmf, 6), "hard", sig * np.sqrt(2 * np.log(n)))
+    assert np.array_equal(y, orc.dwt_filter(c, wt.qmf, 6, fw=False))
+    assert np.array_equal(orc.denoise(x, wt, 6, TI=True, nspin=1), y)
+    yti = orc.denoise(x, wt, 6, TI=True)
+    e, e1, e2 = np.linalg.norm(x - x0), np.linalg.norm(y - x0), np.linalg.norm(yti - x0)
+    assert e2 < e1 < e                                            # denoising helps, cycle spinning helps more
+    # a caller-supplied noise level, soft shrinkage, a lifting wavelet, 2-D
+    wl = wavelet(WT.cdf97, WT.Lifting)
+    ys = orc.denoise(x, wl, 6, kind="soft", sigma=1e-9, TI=True)          # a vanishing threshold returns the signal
+    assert np.max(np.abs(ys - x)) < 1e-6
+    assert np.linalg.norm(orc.denoise(x, wl, 6, kind="hard", sigma=0.05, TI=True) - x0) < e
+    img = rng(7).standard_normal((32, 32))
+    yi = orc.denoise(img, wt, 5, TI=True, nspin=(8, 8))
+    assert yi.shape == (32, 32) and np.abs(yi).max() < np.abs(img).max()
+    with pytest.raises(orc.OracleError):
+        orc.denoise(rng(8).standard_normal((16, 32)), wt, 2)

@@ -15,8 +15,11 @@ from .wt import wavelet
 from .util import maxtransformlevels, maketree, isvalidtree, detailindex, detailrange, detailn
 from .transforms import (modwt, imodwt, maxmodwttransformlevels, dwt, idwt, dwt_, idwt_, wpt, iwpt, wpt_, iwpt_, dwtc, idwtc, dwt_oop_, idwt_oop_,
                          ArgumentError, DimensionMismatch, set_strict_fp, colmajor)
+from . import threshold as Threshold
+from .threshold import (HardTH, SoftTH, SemiSoftTH, SteinTH, BiggestTH, PosTH, NegTH, threshold, threshold_, VisuShrink, denoise, noisest)
 
 __all__ = ["modwt", "imodwt", "maxmodwttransformlevels", "WT", "Util", "wavelet", "maxtransformlevels", "maketree", "isvalidtree", "detailindex",
            "detailrange", "detailn", "dwt", "idwt", "dwt_", "idwt_", "wpt", "iwpt", "wpt_", "iwpt_",
            "dwtc", "idwtc", "dwt_oop_", "idwt_oop_", "ArgumentError", "DimensionMismatch",
-           "set_strict_fp", "colmajor"]
+           "set_strict_fp", "colmajor", "Threshold", "HardTH", "SoftTH", "SemiSoftTH", "SteinTH", "BiggestTH", "PosTH", "NegTH",
+           "threshold", "threshold_", "VisuShrink", "denoise", "noisest"]

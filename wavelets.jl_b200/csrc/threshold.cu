@@ -1,0 +1,327 @@
+// threshold.cu -- SURVEY 8(f) row 2: the main CALLER of the transform path, kept on the device end to end.
+//   threshold!(x, TH, t)                 src/Threshold/threshold_main.jl:35-117   -> k_threshold (elementwise)
+//   noisest(x, wt) = mad!(dr) / 0.6745   src/Threshold/denoising.jl:88-106        -> level-1 dwt + device MAD (radix select)
+//   denoise(x, wt; L, dnt, TI, nspin)    src/Threshold/denoising.jl:22-82         -> wb200_denoise
+// Nothing here synchronises the stream: the noise level stays in device memory and the threshold kernel reads it, so a
+// denoise call is a pure enqueue like the transforms (only wb200_noisest, which must hand a number back, waits).
+// Arithmetic follows Julia's promotion rules: t = sigma * dnt.t is Float64, so comparisons and products with t are done in
+// double and rounded to T on the store; medians are exact order statistics (middle(a, b) = a/2 + b/2 in T).
+#include "common.cuh"
+#include <cmath>
+
+namespace wb {
+
+// ---- threshold!(x, TH, t) -------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ double sgn_of(T v) { return (v > 0) ? 1.0 : ((v < 0) ? -1.0 : (double)v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_threshold(T *__restrict__ x, int64_t n, int kind, double t_host, const double *__restrict__ sigma_dev, double tfac) {
+    const double t = sigma_dev ? __dmul_rn(*sigma_dev, tfac) : t_host;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T v = x[i];
+        T o = v;
+        switch (kind) {
+        case WB200_TH_HARD: if (fabs((double)v) <= t) o = 0; break;
+        case WB200_TH_SOFT: { const double sh = __dsub_rn(fabs((double)v), t); o = (sh < 0) ? (T)0 : (T)__dmul_rn(sgn_of(v), sh); } break;
+        case WB200_TH_SEMISOFT:
+            if ((double)v <= __dmul_rn(2.0, t)) {          // (sic) x[i], not abs(x[i])
+                const double sh = __dsub_rn(fabs((double)v), t);
+                if (sh < 0) o = 0;
+                else if (__dsub_rn(sh, t) < 0) o = (T)__dmul_rn(__dmul_rn(sgn_of(v), sh), 2.0);
+            }
+            break;
+        case WB200_TH_STEIN: {
+            T vv;
+            if constexpr (sizeof(T) == 4) vv = __fmul_rn(v, v); else vv = __dmul_rn(v, v);
+            const double sh = __dsub_rn(1.0, __ddiv_rn(__dmul_rn(t, t), (double)vv));
+            o = (sh < 0) ? (T)0 : (T)__dmul_rn((double)v, sh);
+        } break;
+        case WB200_TH_NEG: if (v < 0) o = 0; break;
+        case WB200_TH_POS: if (v > 0) o = 0; break;
+        default: break;
+        }
+        x[i] = o;
+    }
+}
+
+// ---- exact order statistics by radix select (no sort, no host round trip) --------------------------------------
+// Two ranks are selected together (the two middle elements of an even-length array).  State lives in device memory:
+//   sel[s].prefix / mask : the bits of the answer fixed so far;  sel[s].rank : rank among the still matching elements
+struct SelState { unsigned long long prefix, mask; long long rank; };
+struct SelBuf { SelState st[2]; unsigned int hist[2][256]; };
+
+template <typename T> struct Key;
+template <> struct Key<float> {
+    using U = unsigned int; static constexpr int BITS = 32;
+    static __device__ __forceinline__ unsigned long long of(float v) { const unsigned int u = __float_as_uint(v); return (u & 0x80000000u) ? (unsigned int)~u : (u | 0x80000000u); }
+    static __device__ __forceinline__ float back(unsigned long long k) { const unsigned int u = (unsigned int)k; return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+};
+template <> struct Key<double> {
+    using U = unsigned long long; static constexpr int BITS = 64;
+    static __device__ __forceinline__ unsigned long long of(double v) { const unsigned long long u = (unsigned long long)__double_as_longlong(v); return (u >> 63) ? ~u : (u | 0x8000000000000000ull); }
+    static __device__ __forceinline__ double back(unsigned long long k) { return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k)); }
+};
+
+__global__ void k_sel_init(SelBuf *sb, long long r0, long long r1) {
+    if (threadIdx.x < 2) { sb->st[threadIdx.x].prefix = 0; sb->st[threadIdx.x].mask = 0; sb->st[threadIdx.x].rank = threadIdx.x ? r1 : r0; }
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&sb->hist[0][0])[i] = 0;
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_sel_hist(const T *__restrict__ v, int64_t m, SelBuf *sb, int shift) {
+    __shared__ unsigned int h[2][256];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&h[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned long long p0 = sb->st[0].prefix, m0 = sb->st[0].mask, p1 = sb->st[1].prefix, m1 = sb->st[1].mask;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = Key<T>::of(v[i]);
+        const unsigned int d = (unsigned int)(k >> shift) & 255u;
+        if ((k & m0) == p0) atomicAdd(&h[0][d], 1u);
+        if ((k & m1) == p1) atomicAdd(&h[1][d], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { const unsigned int c = (&h[0][0])[i]; if (c) atomicAdd(&(&sb->hist[0][0])[i], c); }
+}
+__global__ void k_sel_pick(SelBuf *sb, int shift) {
+    const int s = threadIdx.x;
+    if (s < 2) {
+        long long r = sb->st[s].rank;
+        int d = 0;
+        for (; d < 255; ++d) { const long long c = sb->hist[s][d]; if (r < c) break; r -= c; }
+        sb->st[s].rank = r;
+        sb->st[s].prefix |= (unsigned long long)d << shift;
+        sb->st[s].mask |= 0xffull << shift;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) (&sb->hist[0][0])[i] = 0;
+}
+// median = middle(v[k0], v[k1]) = v0/2 + v1/2 in T;  mode 0: store it (T) for the deviation pass;  mode 1: sigma = mad / 0.6745
+template <typename T>
+__global__ void k_sel_finish(const SelBuf *sb, T *med_out, double *sigma_out, int mode) {
+    if (threadIdx.x == 0) {
+        const T a = Key<T>::back(sb->st[0].prefix), b = Key<T>::back(sb->st[1].prefix);
+        T med;
+        if constexpr (sizeof(T) == 4) med = __fadd_rn(__fmul_rn(a, 0.5f), __fmul_rn(b, 0.5f)); else med = __dadd_rn(__dmul_rn(a, 0.5), __dmul_rn(b, 0.5));
+        if (mode == 0) *med_out = med;
+        else *sigma_out = __ddiv_rn((double)med, 0.6745);
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_absdev(T *__restrict__ v, int64_t m, const T *__restrict__ med) {
+    const T c = *med;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        T d;
+        if constexpr (sizeof(T) == 4) d = __fsub_rn(v[i], c); else d = __dsub_rn(v[i], c);
+        v[i] = d < 0 ? -d : d;
+    }
+}
+
+// ---- circular shifts (Base.circshift: out[(i + s) mod n] = in[i] per dimension) and the TI accumulation ----------
+struct Shift3 { int64_t d[3]; int64_t s[3]; };
+template <typename T, int MODE>    // MODE 0: out[o] = in[i];  1: out[o] = out[o] + in[i] (arrayadd! after the inverse shift)
+__global__ void __launch_bounds__(256) k_circshift(T *__restrict__ out, const T *__restrict__ in, const __grid_constant__ Shift3 sh) {
+    const int64_t tot = sh.d[0] * sh.d[1] * sh.d[2];
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx % sh.d[0], r = idx / sh.d[0], j = r % sh.d[1], k = r / sh.d[1];
+        int64_t oi = i + sh.s[0]; if (oi >= sh.d[0]) oi -= sh.d[0];
+        int64_t oj = j + sh.s[1]; if (oj >= sh.d[1]) oj -= sh.d[1];
+        int64_t ok = k + sh.s[2]; if (ok >= sh.d[2]) ok -= sh.d[2];
+        const int64_t o = (ok * sh.d[1] + oj) * sh.d[0] + oi;
+        if (MODE == 0) out[o] = in[idx];
+        else { if constexpr (sizeof(T) == 4) out[o] = __fadd_rn(out[o], in[idx]); else out[o] = __dadd_rn(out[o], in[idx]); }
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_scale(T *__restrict__ y, int64_t n, double s) {   // rmul!(y, 1 / pns)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] = (T)__dmul_rn((double)y[i], s);
+}
+
+static unsigned grid_for_n(int64_t n) {
+    int64_t b = (n + 255) / 256;
+    if (b < 1) b = 1;
+    if (b > 148 * 16) b = 148 * 16;
+    return (unsigned)b;
+}
+
+// device MAD of m contiguous values (destroyed) -> *sigma_dev = mad / 0.6745
+template <typename T>
+static bool device_mad(T *v, int64_t m, SelBuf *sb, T *med, double *sigma_dev, cudaStream_t st) {
+    const unsigned g = grid_for_n(m);
+    for (int round = 0; round < 2; ++round) {
+        {
+            LaunchScope scope("select_init", st);
+            k_sel_init<<<1, 256, 0, st>>>(sb, (long long)((m - 1) / 2), (long long)(m / 2));
+        }
+        for (int shift = Key<T>::BITS - 8; shift >= 0; shift -= 8) {
+            { LaunchScope scope("select_hist", st); k_sel_hist<T><<<g, 256, 0, st>>>(v, m, sb, shift); }
+            { LaunchScope scope("select_pick", st); k_sel_pick<<<1, 256, 0, st>>>(sb, shift); }
+        }
+        { LaunchScope scope("select_finish", st); k_sel_finish<T><<<1, 32, 0, st>>>(sb, med, sigma_dev, round); }
+        if (round == 0) { LaunchScope scope("mad_absdev", st); k_absdev<T><<<g, 256, 0, st>>>(v, m, med); }
+    }
+    return check_launch("device_mad");
+}
+
+} // namespace wb
+
+using namespace wb;
+
+namespace {
+struct WtArgs { int32_t wkind; const double *qmf; int32_t flen; const wb200_lift_step *steps; int32_t nsteps; double norm1, norm2; };
+
+// one transform through the library's own entry points (x != y: the out-of-place forms)
+int32_t xform(void *y, const void *x, int32_t ndim, const int64_t *dims, const WtArgs &w, int32_t L, int32_t fw, int32_t dtype,
+              void *stream, uint32_t flags) {
+    if (w.wkind == 1) return wb200_dwt_filter(y, x, ndim, dims, 1, w.qmf, w.flen, L, fw, dtype, nullptr, 0, stream, flags);
+    return wb200_dwt_lifting(y, x, ndim, dims, 1, w.steps, w.nsteps, w.norm1, w.norm2, L, fw, dtype, nullptr, 0, stream, flags);
+}
+bool check_wt(const WtArgs &w) {
+    if (w.wkind == 0) return true;
+    if (w.wkind == 1) return w.qmf != nullptr && w.flen >= 2;
+    if (w.wkind == 2) return w.steps != nullptr && w.nsteps >= 1;
+    return false;
+}
+
+// noisest on the device: *sigma_dev = mad(y[n1/2 : n1]) / 0.6745, y = level-1 transform of x (or x itself).  tmp: tot elements.
+template <typename T>
+int32_t noisest_dev(double *sigma_dev, const T *x, int32_t ndim, const int64_t *dims, int64_t tot, const WtArgs &w, T *tmp,
+                    SelBuf *sb, T *med, int32_t dtype, cudaStream_t st, uint32_t flags) {
+    const int64_t n1 = dims[0], lo = (int64_t)std::nearbyint((double)n1 / 2 + 1) - 1, m = n1 - lo;   // round(Int, .): ties to even
+    if (m < 1) { set_error("noisest: no detail coefficients (size(x,1) = %lld)", (long long)n1); return WB200_EDIMS; }
+    if (w.wkind == 0) {
+        if (cudaMemcpyAsync(tmp, x + lo, sizeof(T) * (size_t)m, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { (void)cudaGetLastError(); return WB200_ECUDA; }
+    } else {
+        const int32_t rc = xform(tmp, x, ndim, dims, w, 1, 1, dtype, (void *)st, flags);
+        if (rc != WB200_OK) return rc;
+        if (lo > 0 && cudaMemcpyAsync(tmp, tmp + lo, sizeof(T) * (size_t)m, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { (void)cudaGetLastError(); return WB200_ECUDA; }
+    }
+    // (the copy ranges [lo, lo+m) and [0, m) may overlap only if lo < m, i.e. never: lo = n1/2 = m)
+    return device_mad<T>(tmp, m, sb, med, sigma_dev, st) ? WB200_OK : WB200_ECUDA;
+}
+
+template <typename T>
+int32_t denoise_t(T *y, const T *x, int32_t ndim, const int64_t *dims, const WtArgs &w, int32_t L, int32_t th_kind, double tfac,
+                  double sigma, int32_t TI, const int32_t *nspin, int32_t dtype, cudaStream_t st, uint32_t flags) {
+    int64_t tot = 1;
+    for (int a = 0; a < ndim; ++a) tot *= dims[a];
+    for (int a = 1; a < ndim; ++a) if (dims[a] != dims[0]) { set_error("array must be square/cube"); return WB200_ENOTCUBE; }
+    if (tot == 0) return WB200_OK;
+    if (TI && w.wkind == 0) { set_error("TI not supported with wt=nothing"); return WB200_EARG; }
+    const bool est = sigma != sigma;
+    // scratch: TI needs three arrays (z, xt, w), plain needs one; the selection state and two scalars ride behind them
+    const size_t arr = (((size_t)tot * sizeof(T)) + 255) & ~(size_t)255;
+    const int narr = TI ? 3 : 1;
+    char *pool = nullptr;
+    keep_pool_memory();
+    if (cudaMallocAsync((void **)&pool, narr * arr + 4096, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(denoise scratch) failed"); return WB200_ECUDA; }
+    T *a0 = (T *)pool, *a1 = (T *)(pool + arr), *a2 = (T *)(pool + 2 * arr);
+    SelBuf *sb = (SelBuf *)(pool + narr * arr);
+    T *med = (T *)(pool + narr * arr + 3072);
+    double *sig = (double *)(pool + narr * arr + 3072 + 64);
+    int32_t rc = WB200_OK;
+    const unsigned g = grid_for_n(tot);
+    if (est) rc = noisest_dev<T>(sig, x, ndim, dims, tot, w, a0, sb, med, dtype, st, flags);
+    auto thr = [&](T *c) {
+        LaunchScope scope("threshold", st);
+        k_threshold<T><<<g, 256, 0, st>>>(c, tot, th_kind, sigma * tfac, est ? sig : nullptr, tfac);
+    };
+    if (rc == WB200_OK && !TI) {
+        if (w.wkind == 0) {
+            if (y != x && cudaMemcpyAsync(y, x, sizeof(T) * (size_t)tot, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { (void)cudaGetLastError(); rc = WB200_ECUDA; }
+            if (rc == WB200_OK) thr(y);
+        } else {
+            rc = xform(a0, x, ndim, dims, w, L, 1, dtype, (void *)st, flags);
+            if (rc == WB200_OK) { thr(a0); rc = xform(y, a0, ndim, dims, w, L, 0, dtype, (void *)st, flags); }
+        }
+    } else if (rc == WB200_OK) {
+        int64_t pns = 1;
+        for (int a = 0; a < ndim; ++a) pns *= nspin[a] > 0 ? nspin[a] : 1;
+        if (cudaMemsetAsync(y, 0, sizeof(T) * (size_t)tot, st) != cudaSuccess) { (void)cudaGetLastError(); rc = WB200_ECUDA; }
+        for (int64_t it = 0; it < pns && rc == WB200_OK; ++it) {
+            Shift3 fwd{}, bwd{};
+            int64_t r = it;
+            for (int a = 0; a < 3; ++a) {
+                const int64_t d = a < ndim ? dims[a] : 1;
+                int64_t s = 0;
+                if (a < ndim) { const int64_t ns = nspin[a] > 0 ? nspin[a] : 1; s = (ndim == 1) ? it : r % ns; r /= ns; }
+                s %= d;
+                fwd.d[a] = bwd.d[a] = d; fwd.s[a] = s; bwd.s[a] = (d - s) % d;
+            }
+            { LaunchScope scope("circshift", st); k_circshift<T, 0><<<g, 256, 0, st>>>(a0, x, fwd); }
+            rc = xform(a1, a0, ndim, dims, w, L, 1, dtype, (void *)st, flags);
+            if (rc != WB200_OK) break;
+            thr(a1);
+            rc = xform(a0, a1, ndim, dims, w, L, 0, dtype, (void *)st, flags);
+            if (rc != WB200_OK) break;
+            { LaunchScope scope("circshift_add", st); k_circshift<T, 1><<<g, 256, 0, st>>>(y, a0, bwd); }
+        }
+        if (rc == WB200_OK) { LaunchScope scope("scale", st); k_scale<T><<<g, 256, 0, st>>>(y, tot, 1.0 / (double)pns); }
+        (void)a2;
+    }
+    if (rc == WB200_OK && !check_launch("denoise")) rc = WB200_ECUDA;
+    cudaFreeAsync(pool, st);
+    return rc;
+}
+} // namespace
+
+extern "C" int32_t wb200_threshold(void *x, int64_t count, int32_t kind, double t, int32_t dtype, void *stream) {
+    if (dtype != WB200_F32 && dtype != WB200_F64) { set_error("threshold supports Float32/Float64"); return WB200_EDTYPE; }
+    if (kind < WB200_TH_HARD || kind > WB200_TH_POS) { set_error("unknown threshold kind %d", kind); return WB200_EARG; }
+    if (count < 0 || (count > 0 && x == nullptr)) { set_error("bad array"); return WB200_EARG; }
+    if ((kind <= WB200_TH_STEIN) && !(t >= 0)) { set_error("threshold must be >= 0"); return WB200_EARG; }     // @assert t >= 0
+    if (count == 0) return WB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        LaunchScope scope("threshold", st);
+        if (dtype == WB200_F64) k_threshold<double><<<grid_for_n(count), 256, 0, st>>>((double *)x, count, kind, t, nullptr, 1.0);
+        else                    k_threshold<float><<<grid_for_n(count), 256, 0, st>>>((float *)x, count, kind, t, nullptr, 1.0);
+    }
+    return check_launch("threshold") ? WB200_OK : WB200_ECUDA;
+}
+
+extern "C" int32_t wb200_noisest(double *sigma_out, const void *x, int32_t ndim, const int64_t *dims, int32_t wkind,
+                                 const double *qmf, int32_t flen, const wb200_lift_step *steps, int32_t nsteps, double norm1,
+                                 double norm2, int32_t dtype, void *stream, uint32_t flags) {
+    if (dtype != WB200_F32 && dtype != WB200_F64) { set_error("noisest supports Float32/Float64"); return WB200_EDTYPE; }
+    if (sigma_out == nullptr || x == nullptr || dims == nullptr || ndim < 1 || ndim > 3) { set_error("bad argument"); return WB200_EARG; }
+    const WtArgs w{wkind, qmf, flen, steps, nsteps, norm1, norm2};
+    if (!check_wt(w)) { set_error("bad wavelet description"); return WB200_EARG; }
+    int64_t tot = 1;
+    for (int a = 0; a < ndim; ++a) { if (dims[a] < 1) { set_error("dims[%d] = %lld", a, (long long)dims[a]); return WB200_EDIMS; } tot *= dims[a]; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t esz = dtype == WB200_F64 ? 8 : 4;
+    const size_t arr = (((size_t)tot * esz) + 255) & ~(size_t)255;
+    char *pool = nullptr;
+    keep_pool_memory();
+    if (cudaMallocAsync((void **)&pool, arr + 4096, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(noisest scratch) failed"); return WB200_ECUDA; }
+    SelBuf *sb = (SelBuf *)(pool + arr);
+    double *sig = (double *)(pool + arr + 3072 + 64);
+    int32_t rc;
+    if (dtype == WB200_F64) rc = noisest_dev<double>(sig, (const double *)x, ndim, dims, tot, w, (double *)pool, sb, (double *)(pool + arr + 3072), dtype, st, flags);
+    else                    rc = noisest_dev<float>(sig, (const float *)x, ndim, dims, tot, w, (float *)pool, sb, (float *)(pool + arr + 3072), dtype, st, flags);
+    if (rc == WB200_OK) {
+        if (cudaMemcpyAsync(sigma_out, sig, sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+            (void)cudaGetLastError(); set_error("noisest: copy of the result failed"); rc = WB200_ECUDA;
+        }
+    }
+    cudaFreeAsync(pool, st);
+    return rc;
+}
+
+extern "C" int32_t wb200_denoise(void *y, const void *x, int32_t ndim, const int64_t *dims, int32_t wkind, const double *qmf,
+                                 int32_t flen, const wb200_lift_step *steps, int32_t nsteps, double norm1, double norm2, int32_t L,
+                                 int32_t th_kind, double tfac, double sigma, int32_t TI, const int32_t *nspin, int32_t dtype,
+                                 void *stream, uint32_t flags) {
+    if (dtype != WB200_F32 && dtype != WB200_F64) { set_error("denoise supports Float32/Float64"); return WB200_EDTYPE; }
+    if (y == nullptr || x == nullptr || dims == nullptr || ndim < 1 || ndim > 3 || (TI && nspin == nullptr)) { set_error("bad argument"); return WB200_EARG; }
+    if (th_kind < WB200_TH_HARD || th_kind > WB200_TH_POS) { set_error("unknown threshold kind %d", th_kind); return WB200_EARG; }
+    const WtArgs w{wkind, qmf, flen, steps, nsteps, norm1, norm2};
+    if (!check_wt(w)) { set_error("bad wavelet description"); return WB200_EARG; }
+    for (int a = 0; a < ndim; ++a) if (dims[a] < 1) { set_error("dims[%d] = %lld", a, (long long)dims[a]); return WB200_EDIMS; }
+    if (y == x && w.wkind != 0) { set_error("denoise: y must not alias x"); return WB200_EALIAS; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == WB200_F64) return denoise_t<double>((double *)y, (const double *)x, ndim, dims, w, L, th_kind, tfac, sigma, TI, nspin, dtype, st, flags);
+    return denoise_t<float>((float *)y, (const float *)x, ndim, dims, w, L, th_kind, tfac, sigma, TI, nspin, dtype, st, flags);
+}

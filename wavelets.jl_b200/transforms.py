@@ -48,6 +48,10 @@ def set_strict_fp(on: bool) -> None:
     _flags = (_flags | _lib.FLAG_STRICT_FP) if on else (_flags & ~_lib.FLAG_STRICT_FP)
 
 
+def _flags_value() -> int:
+    return _flags
+
+
 def _force_generic(on: bool) -> None:
     global _flags
     _flags = (_flags | _lib.FLAG_FORCE_GENERIC) if on else (_flags & ~_lib.FLAG_FORCE_GENERIC)
