@@ -491,6 +491,15 @@ def run_extras(L, wb, _lib, dev, stream, args):
     res["denoise_sym5_16777216_f32_L6"] = {"msamples_per_s": nd_ / (ms * 1e-3) / 1e6, "ms_per_call": ms, "ms_per_pair": ms,
                                            "achieved_gbs_pair": gbs, "frac_of_hbm_peak": gbs / peak,
                                            "note": "bytes = 2 n sizeof(T) (read x, write y); the pipeline itself makes four passes"}
+    del xd
+    # the same with translation-invariant cycle spinning on an image: 1024^2, 8 x 8 = 64 shifted copies run as one batch
+    xi = torch.randn((1024, 1024), dtype=torch.float32, device=dev)
+    ms = timed_pair(lambda: wb.denoise(xi, TI=True), lambda y: y)
+    res["denoise_TI_sym5_1024x1024_f32_64spins"] = {"msamples_per_s": 1024 * 1024 / (ms * 1e-3) / 1e6, "ms_per_call": ms, "ms_per_pair": ms,
+                                                    "achieved_gbs_pair": 2.0 * 1024 * 1024 * 4 / (ms * 1e-3) / 1e9,
+                                                    "frac_of_hbm_peak": 2.0 * 1024 * 1024 * 4 / (ms * 1e-3) / 1e9 / peak,
+                                                    "spin_msamples_per_s": 64 * 1024 * 1024 / (ms * 1e-3) / 1e6,
+                                                    "note": "64 shifted dwt / threshold / idwt triples per call"}
     return res
 
 

@@ -811,3 +811,18 @@ def test_denoise_defaults_errors_and_scale(dev):
     assert abs(wb.noisest(noisy) - 0.05) < 2e-3
     den = wb.denoise(noisy, TI=True, nspin=4)
     assert float((den - clean).norm()) < 0.25 * float((noisy - clean).norm())
+
+
+@pytest.mark.parametrize("chunk_mb", ["0", "1"])
+def test_denoise_ti_spin_chunks(dev, monkeypatch, chunk_mb):
+    """the spins of a TI denoise are batched; whatever the chunking, the accumulation order is the reference's"""
+    monkeypatch.setenv("WB200_DENOISE_CHUNK_MB", chunk_mb)      # 0: one spin per batch; 1: a few
+    wf = wavelet(WT.sym5)
+    wb.set_strict_fp(True)
+    try:
+        for shape, nspin in (((4096,), 8), ((128, 128), (4, 4))):
+            x = (_doppler(shape[0]).reshape((-1,) + (1,) * (len(shape) - 1)) + 0.1 * rng(1).standard_normal(shape)).astype(np.float32)
+            got = to_np(wb.denoise(to_gpu(x, dev), wf, TI=True, nspin=nspin))
+            assert np.array_equal(got, orc.denoise(x, wf, 6, TI=True, nspin=nspin))
+    finally:
+        wb.set_strict_fp(False)

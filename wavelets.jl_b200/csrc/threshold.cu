@@ -8,6 +8,7 @@
 // double and rounded to T on the store; medians are exact order statistics (middle(a, b) = a/2 + b/2 in T).
 #include "common.cuh"
 #include <cmath>
+#include <cstdlib>
 
 namespace wb {
 
@@ -132,6 +133,51 @@ __global__ void __launch_bounds__(256) k_circshift(T *__restrict__ out, const T 
         else { if constexpr (sizeof(T) == 4) out[o] = __fadd_rn(out[o], in[idx]); else out[o] = __dadd_rn(out[o], in[idx]); }
     }
 }
+// Translation-invariant denoising runs its nspin^d shifted copies as ONE batch: all shifted copies are laid out back to back
+// (k_spin_scatter), transformed / thresholded / inverted by the batched entry points, and summed back in spin order with the
+// inverse shifts (k_spin_gather_add) -- the same per-element arithmetic and the same accumulation order as the reference's
+// loop over spins (denoising.jl:36-64), in ~6 launches per chunk of spins instead of ~6 per spin.
+struct SpinPlan { int64_t d[3]; int32_t ns[3]; int32_t ndim; };
+__device__ __forceinline__ void spin_shift(const SpinPlan &p, int64_t spin, int64_t (&s)[3]) {
+    int64_t r = spin;
+    for (int a = 0; a < 3; ++a) {
+        int64_t v = 0;
+        if (a < p.ndim) { if (p.ndim == 1) v = spin; else { v = r % p.ns[a]; r /= p.ns[a]; } }
+        s[a] = v % p.d[a];
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_spin_scatter(T *__restrict__ Z, const T *__restrict__ x, const __grid_constant__ SpinPlan p, int64_t s0, int cnt) {
+    const int64_t tot = p.d[0] * p.d[1] * p.d[2];
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tot * cnt; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = idx % tot, sp = idx / tot;
+        int64_t s[3];
+        spin_shift(p, s0 + sp, s);
+        const int64_t i = e % p.d[0], r = e / p.d[0], j = r % p.d[1], k = r / p.d[1];
+        int64_t oi = i + s[0]; if (oi >= p.d[0]) oi -= p.d[0];
+        int64_t oj = j + s[1]; if (oj >= p.d[1]) oj -= p.d[1];
+        int64_t ok = k + s[2]; if (ok >= p.d[2]) ok -= p.d[2];
+        Z[sp * tot + (ok * p.d[1] + oj) * p.d[0] + oi] = x[e];           // z = circshift(x, shift)
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_spin_gather_add(T *__restrict__ y, const T *__restrict__ Z, const __grid_constant__ SpinPlan p, int64_t s0, int cnt) {
+    const int64_t tot = p.d[0] * p.d[1] * p.d[2];
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < tot; o += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = o % p.d[0], r = o / p.d[0], j = r % p.d[1], k = r / p.d[1];
+        T acc = y[o];
+        for (int sp = 0; sp < cnt; ++sp) {                                 // arrayadd!(y, circshift(z, -shift)), spins in order
+            int64_t s[3];
+            spin_shift(p, s0 + sp, s);
+            int64_t si = i + s[0]; if (si >= p.d[0]) si -= p.d[0];
+            int64_t sj = j + s[1]; if (sj >= p.d[1]) sj -= p.d[1];
+            int64_t sk = k + s[2]; if (sk >= p.d[2]) sk -= p.d[2];
+            const T w = Z[(int64_t)sp * tot + (sk * p.d[1] + sj) * p.d[0] + si];
+            if constexpr (sizeof(T) == 4) acc = __fadd_rn(acc, w); else acc = __dadd_rn(acc, w);
+        }
+        y[o] = acc;
+    }
+}
 template <typename T>
 __global__ void __launch_bounds__(256) k_scale(T *__restrict__ y, int64_t n, double s) {   // rmul!(y, 1 / pns)
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -173,9 +219,9 @@ struct WtArgs { int32_t wkind; const double *qmf; int32_t flen; const wb200_lift
 
 // one transform through the library's own entry points (x != y: the out-of-place forms)
 int32_t xform(void *y, const void *x, int32_t ndim, const int64_t *dims, const WtArgs &w, int32_t L, int32_t fw, int32_t dtype,
-              void *stream, uint32_t flags) {
-    if (w.wkind == 1) return wb200_dwt_filter(y, x, ndim, dims, 1, w.qmf, w.flen, L, fw, dtype, nullptr, 0, stream, flags);
-    return wb200_dwt_lifting(y, x, ndim, dims, 1, w.steps, w.nsteps, w.norm1, w.norm2, L, fw, dtype, nullptr, 0, stream, flags);
+              void *stream, uint32_t flags, int64_t batch = 1) {
+    if (w.wkind == 1) return wb200_dwt_filter(y, x, ndim, dims, batch, w.qmf, w.flen, L, fw, dtype, nullptr, 0, stream, flags);
+    return wb200_dwt_lifting(y, x, ndim, dims, batch, w.steps, w.nsteps, w.norm1, w.norm2, L, fw, dtype, nullptr, 0, stream, flags);
 }
 bool check_wt(const WtArgs &w) {
     if (w.wkind == 0) return true;
@@ -211,12 +257,23 @@ int32_t denoise_t(T *y, const T *x, int32_t ndim, const int64_t *dims, const WtA
     if (TI && w.wkind == 0) { set_error("TI not supported with wt=nothing"); return WB200_EARG; }
     const bool est = sigma != sigma;
     // scratch: TI needs three arrays (z, xt, w), plain needs one; the selection state and two scalars ride behind them
-    const size_t arr = (((size_t)tot * sizeof(T)) + 255) & ~(size_t)255;
-    const int narr = TI ? 3 : 1;
+    int64_t pns = 1, chunk = 1;
+    if (TI) {
+        for (int a = 0; a < ndim; ++a) pns *= nspin[a] > 0 ? nspin[a] : 1;
+        // spins per batch: two batch buffers of `chunk` shifted copies each, at most ~1 GiB together
+        const char *e = std::getenv("WB200_DENOISE_CHUNK_MB");
+        const size_t budget = (size_t)(e ? std::atoll(e) : 512) << 20;
+        chunk = (int64_t)(budget / ((size_t)tot * sizeof(T)));
+        if (chunk < 1) chunk = 1;
+        if (chunk > pns) chunk = pns;
+        if (chunk > 4096) chunk = 4096;
+    }
+    const size_t arr = (((size_t)tot * (size_t)chunk * sizeof(T)) + 255) & ~(size_t)255;
+    const int narr = TI ? 2 : 1;
     char *pool = nullptr;
     keep_pool_memory();
     if (cudaMallocAsync((void **)&pool, narr * arr + 4096, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(denoise scratch) failed"); return WB200_ECUDA; }
-    T *a0 = (T *)pool, *a1 = (T *)(pool + arr), *a2 = (T *)(pool + 2 * arr);
+    T *a0 = (T *)pool, *a1 = (T *)(pool + (narr > 1 ? arr : 0));
     SelBuf *sb = (SelBuf *)(pool + narr * arr);
     T *med = (T *)(pool + narr * arr + 3072);
     double *sig = (double *)(pool + narr * arr + 3072 + 64);
@@ -236,29 +293,25 @@ int32_t denoise_t(T *y, const T *x, int32_t ndim, const int64_t *dims, const WtA
             if (rc == WB200_OK) { thr(a0); rc = xform(y, a0, ndim, dims, w, L, 0, dtype, (void *)st, flags); }
         }
     } else if (rc == WB200_OK) {
-        int64_t pns = 1;
-        for (int a = 0; a < ndim; ++a) pns *= nspin[a] > 0 ? nspin[a] : 1;
+        SpinPlan sp{};
+        sp.ndim = ndim;
+        for (int a = 0; a < 3; ++a) { sp.d[a] = a < ndim ? dims[a] : 1; sp.ns[a] = (a < ndim && nspin[a] > 0) ? nspin[a] : 1; }
         if (cudaMemsetAsync(y, 0, sizeof(T) * (size_t)tot, st) != cudaSuccess) { (void)cudaGetLastError(); rc = WB200_ECUDA; }
-        for (int64_t it = 0; it < pns && rc == WB200_OK; ++it) {
-            Shift3 fwd{}, bwd{};
-            int64_t r = it;
-            for (int a = 0; a < 3; ++a) {
-                const int64_t d = a < ndim ? dims[a] : 1;
-                int64_t s = 0;
-                if (a < ndim) { const int64_t ns = nspin[a] > 0 ? nspin[a] : 1; s = (ndim == 1) ? it : r % ns; r /= ns; }
-                s %= d;
-                fwd.d[a] = bwd.d[a] = d; fwd.s[a] = s; bwd.s[a] = (d - s) % d;
+        for (int64_t s0 = 0; s0 < pns && rc == WB200_OK; s0 += chunk) {
+            const int cnt = (int)((pns - s0 < chunk) ? (pns - s0) : chunk);
+            const unsigned gb = grid_for_n(tot * cnt);
+            { LaunchScope scope("spin_scatter", st); k_spin_scatter<T><<<gb, 256, 0, st>>>(a0, x, sp, s0, cnt); }
+            rc = xform(a1, a0, ndim, dims, w, L, 1, dtype, (void *)st, flags, cnt);
+            if (rc != WB200_OK) break;
+            {
+                LaunchScope scope("threshold", st);
+                k_threshold<T><<<gb, 256, 0, st>>>(a1, tot * cnt, th_kind, sigma * tfac, est ? sig : nullptr, tfac);
             }
-            { LaunchScope scope("circshift", st); k_circshift<T, 0><<<g, 256, 0, st>>>(a0, x, fwd); }
-            rc = xform(a1, a0, ndim, dims, w, L, 1, dtype, (void *)st, flags);
+            rc = xform(a0, a1, ndim, dims, w, L, 0, dtype, (void *)st, flags, cnt);
             if (rc != WB200_OK) break;
-            thr(a1);
-            rc = xform(a0, a1, ndim, dims, w, L, 0, dtype, (void *)st, flags);
-            if (rc != WB200_OK) break;
-            { LaunchScope scope("circshift_add", st); k_circshift<T, 1><<<g, 256, 0, st>>>(y, a0, bwd); }
+            { LaunchScope scope("spin_gather_add", st); k_spin_gather_add<T><<<g, 256, 0, st>>>(y, a0, sp, s0, cnt); }
         }
         if (rc == WB200_OK) { LaunchScope scope("scale", st); k_scale<T><<<g, 256, 0, st>>>(y, tot, 1.0 / (double)pns); }
-        (void)a2;
     }
     if (rc == WB200_OK && !check_launch("denoise")) rc = WB200_ECUDA;
     cudaFreeAsync(pool, st);
