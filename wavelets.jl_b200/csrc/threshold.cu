@@ -118,21 +118,7 @@ __global__ void __launch_bounds__(256) k_absdev(T *__restrict__ v, int64_t m, co
     }
 }
 
-// ---- circular shifts (Base.circshift: out[(i + s) mod n] = in[i] per dimension) and the TI accumulation ----------
-struct Shift3 { int64_t d[3]; int64_t s[3]; };
-template <typename T, int MODE>    // MODE 0: out[o] = in[i];  1: out[o] = out[o] + in[i] (arrayadd! after the inverse shift)
-__global__ void __launch_bounds__(256) k_circshift(T *__restrict__ out, const T *__restrict__ in, const __grid_constant__ Shift3 sh) {
-    const int64_t tot = sh.d[0] * sh.d[1] * sh.d[2];
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = idx % sh.d[0], r = idx / sh.d[0], j = r % sh.d[1], k = r / sh.d[1];
-        int64_t oi = i + sh.s[0]; if (oi >= sh.d[0]) oi -= sh.d[0];
-        int64_t oj = j + sh.s[1]; if (oj >= sh.d[1]) oj -= sh.d[1];
-        int64_t ok = k + sh.s[2]; if (ok >= sh.d[2]) ok -= sh.d[2];
-        const int64_t o = (ok * sh.d[1] + oj) * sh.d[0] + oi;
-        if (MODE == 0) out[o] = in[idx];
-        else { if constexpr (sizeof(T) == 4) out[o] = __fadd_rn(out[o], in[idx]); else out[o] = __dadd_rn(out[o], in[idx]); }
-    }
-}
+// ---- translation-invariant cycle spinning (Base.circshift: out[(i + s) mod n] = in[i] per dimension) ---------------
 // Translation-invariant denoising runs its nspin^d shifted copies as ONE batch: all shifted copies are laid out back to back
 // (k_spin_scatter), transformed / thresholded / inverted by the batched entry points, and summed back in spin order with the
 // inverse shifts (k_spin_gather_add) -- the same per-element arithmetic and the same accumulation order as the reference's
