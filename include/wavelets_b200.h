@@ -123,7 +123,7 @@ int32_t wb200_imodwt(void *x, const void *xw, int64_t n, int64_t batch, const do
 int32_t wb200_maxmodwttransformlevels(int64_t n);                             /* non_dyadic.jl:24-25 */
 
 /* ---- thresholding and denoising: the main caller of the transforms, device end to end ----
- * threshold!(x, TH, t)            src/Threshold/threshold_main.jl:35-117 (BiggestTH is not on the device path yet)
+ * threshold!(x, TH, t)            src/Threshold/threshold_main.jl:21-117
  * noisest(x, wt)                  src/Threshold/denoising.jl:88-106: level-1 transform, MAD of y[n1/2+1 : n1] (linear
  *                                 indices: the second half of the FIRST column, whatever ndim) over 0.6745.  Returns the
  *                                 number, so it waits for the stream.
@@ -138,6 +138,9 @@ int32_t wb200_maxmodwttransformlevels(int64_t n);                             /*
 #define WB200_TH_NEG 4
 #define WB200_TH_POS 5
 int32_t wb200_threshold(void *x, int64_t count, int32_t kind, double t, int32_t dtype, void *stream);
+/* threshold!(x, BiggestTH(), m): keep the m entries of largest magnitude (threshold_main.jl:21-33); ties at the cut are
+ * dropped in index order (the reference's unstable QuickSort leaves that order unspecified). */
+int32_t wb200_threshold_biggest(void *x, int64_t count, int64_t m, int32_t dtype, void *stream);
 int32_t wb200_noisest(double *sigma_out, const void *x, int32_t ndim, const int64_t *dims, int32_t wkind,
                       const double *qmf, int32_t flen, const wb200_lift_step *steps, int32_t nsteps, double norm1,
                       double norm2, int32_t dtype, void *stream, uint32_t flags);

@@ -131,6 +131,11 @@ function Wavelets.Threshold.threshold!(x::CuArray{T}, TH::Wavelets.Threshold.THT
                pointer(x), length(x), th_code(TH), Float64(t), dtype_code(T), CUDA.stream().handle)
     check(rc); x
 end
+function Wavelets.Threshold.threshold!(x::CuArray{T}, ::Wavelets.Threshold.BiggestTH, m::Int) where {T<:Union{Float32,Float64}}
+    rc = ccall((:wb200_threshold_biggest, LIB), Int32, (CuPtr{Cvoid}, Int64, Int64, Int32, Ptr{Cvoid}),
+               pointer(x), length(x), m, dtype_code(T), CUDA.stream().handle)
+    check(rc); x
+end
 # wkind / qmf / steps of a wavelet (nothing, OrthoFilter, GLS)
 wt_args(::Nothing) = (Int32(0), Float64[], LiftStep[], 0.0, 0.0)
 wt_args(f::OrthoFilter) = (Int32(1), Vector{Float64}(f.qmf), LiftStep[], 0.0, 0.0)

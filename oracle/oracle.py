@@ -239,6 +239,14 @@ def threshold(x, kind, t=0.0):
     return y
 
 
+def threshold_biggest(x, m):
+    """Reference `threshold(x, BiggestTH(), m)` (ties at the cut dropped in index order)."""
+    y = np.ascontiguousarray(np.array(x, copy=True).ravel(order="F"))
+    sfx, ct = _sfx(y.dtype)
+    getattr(lib(), "orc_threshold_biggest" + sfx)(y.ctypes.data_as(C.c_void_p), C.c_int64(y.size), C.c_int64(int(m)))
+    return y.reshape(np.shape(x), order="F")
+
+
 def noisest(x, wt):
     x = _fcopy(x)
     sfx, ct = _sfx(x.dtype)

@@ -726,8 +726,6 @@ def test_threshold_vs_oracle(dev, dtype, kind):
     x2 = to_gpu(x.reshape(50, 100), dev)
     assert wb.threshold_(x2, TH[kind](), *args) is x2
     assert np.array_equal(to_np(x2), orc.threshold(x.reshape(50, 100), kind, 2.0), equal_nan=True)
-    with pytest.raises(NotImplementedError):
-        wb.threshold(to_gpu(x, dev), wb.BiggestTH(), 3)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -801,7 +799,7 @@ def test_denoise_defaults_errors_and_scale(dev):
         wb.denoise(to_gpu(rng(1).standard_normal((16, 32)), dev))
     with pytest.raises(RuntimeError, match="TI not supported"):
         wb.denoise(xg, None, TI=True)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError):
         wb.denoise(xg, dnt=wb.VisuShrink(wb.BiggestTH(), 1.0))
     # N = 2^20, Float32: the noise level is recovered and cycle-spun denoising removes most of the noise
     N = 1 << 20
@@ -826,3 +824,23 @@ def test_denoise_ti_spin_chunks(dev, monkeypatch, chunk_mb):
             assert np.array_equal(got, orc.denoise(x, wf, 6, TI=True, nspin=nspin))
     finally:
         wb.set_strict_fp(False)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_threshold_biggest_vs_oracle(dev, dtype):
+    """threshold!(x, BiggestTH(), m): radix select of the cut magnitude; ties at the cut go in index order"""
+    cases = [rng(21).standard_normal(5000) * 2, np.round(rng(22).standard_normal(4000) * 2), np.zeros(64), rng(23).standard_normal((64, 32))]
+    for x in cases:
+        x = x.astype(dtype)
+        n = x.size
+        for m in (0, 1, 2, n // 3, n - 1, n, n + 7):
+            y = wb.threshold(to_gpu(x, dev), wb.BiggestTH(), m)
+            assert np.array_equal(to_np(y), orc.threshold_biggest(x, m)), (x.shape, m)
+    xb = torch.randn(1 << 22, device=dev, dtype=torch.float32 if dtype == np.float32 else torch.float64)
+    m = 12345
+    yb = wb.threshold(xb, wb.BiggestTH(), m)
+    assert int((yb != 0).sum()) == m
+    kept = xb.abs() >= torch.topk(xb.abs(), m).values.min()
+    assert torch.equal(yb, torch.where(kept, xb, torch.zeros_like(xb)))
+    with pytest.raises(TypeError):
+        wb.threshold(xb, wb.BiggestTH(), 2.5)

@@ -295,3 +295,12 @@ def test_noisest_and_denoise_properties():
     assert yi.shape == (32, 32) and np.abs(yi).max() < np.abs(img).max()
     with pytest.raises(orc.OracleError):
         orc.denoise(rng(8).standard_normal((16, 32)), wt, 2)
+
+
+def test_threshold_biggest_definition():
+    for x in (rng(9).standard_normal(200) * 2, np.round(rng(10).standard_normal(300) * 2)):      # the second has many ties
+        for m in (0, 1, 17, 150, len(x), len(x) + 5):
+            ref = x.copy()
+            ref[np.argsort(np.abs(x), kind="stable")[: max(0, len(x) - m)]] = 0
+            assert np.array_equal(orc.threshold_biggest(x, m), ref)
+            assert np.count_nonzero(orc.threshold_biggest(x, m)) <= m

@@ -29,7 +29,7 @@ SYMBOLS = [
     "wb200_last_error_string", "wb200_version", "wb200_launch_count",
     "wb200_profile_enable", "wb200_profile_collect",
     "wb200_modwt", "wb200_imodwt", "wb200_maxmodwttransformlevels",
-    "wb200_threshold", "wb200_noisest", "wb200_denoise",
+    "wb200_threshold", "wb200_threshold_biggest", "wb200_noisest", "wb200_denoise",
 ]
 
 
@@ -66,6 +66,8 @@ def lib() -> C.CDLL:
     L.wb200_maxmodwttransformlevels.restype = i32
     L.wb200_threshold.argtypes = [vp, i64, i32, C.c_double, i32, vp]
     L.wb200_threshold.restype = i32
+    L.wb200_threshold_biggest.argtypes = [vp, i64, i64, i32, vp]
+    L.wb200_threshold_biggest.restype = i32
     L.wb200_noisest.argtypes = [pd, vp, i32, C.POINTER(i64), i32, pd, i32, C.POINTER(LiftStep), i32, C.c_double, C.c_double, i32, vp, u32]
     L.wb200_noisest.restype = i32
     L.wb200_denoise.argtypes = [vp, vp, i32, C.POINTER(i64), i32, pd, i32, C.POINTER(LiftStep), i32, C.c_double, C.c_double, i32,

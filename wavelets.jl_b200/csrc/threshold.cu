@@ -68,7 +68,7 @@ __global__ void k_sel_init(SelBuf *sb, long long r0, long long r1) {
     if (threadIdx.x < 2) { sb->st[threadIdx.x].prefix = 0; sb->st[threadIdx.x].mask = 0; sb->st[threadIdx.x].rank = threadIdx.x ? r1 : r0; }
     for (int i = threadIdx.x; i < 512; i += blockDim.x) (&sb->hist[0][0])[i] = 0;
 }
-template <typename T>
+template <typename T, bool ABS>
 __global__ void __launch_bounds__(256)
 k_sel_hist(const T *__restrict__ v, int64_t m, SelBuf *sb, int shift) {
     __shared__ unsigned int h[2][256];
@@ -76,7 +76,7 @@ k_sel_hist(const T *__restrict__ v, int64_t m, SelBuf *sb, int shift) {
     __syncthreads();
     const unsigned long long p0 = sb->st[0].prefix, m0 = sb->st[0].mask, p1 = sb->st[1].prefix, m1 = sb->st[1].mask;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long k = Key<T>::of(v[i]);
+        const unsigned long long k = Key<T>::of(ABS ? (v[i] < 0 ? -v[i] : v[i]) : v[i]);
         const unsigned int d = (unsigned int)(k >> shift) & 255u;
         if ((k & m0) == p0) atomicAdd(&h[0][d], 1u);
         if ((k & m1) == p1) atomicAdd(&h[1][d], 1u);
@@ -170,6 +170,47 @@ __global__ void __launch_bounds__(256) k_scale(T *__restrict__ y, int64_t n, dou
         y[i] = (T)__dmul_rn((double)y[i], s);
 }
 
+// ---- threshold!(x, BiggestTH(), m): keep the m entries of largest magnitude (threshold_main.jl:21-33) ----------------------
+// v = the (n-m)-th smallest |x| (0-based) by radix select; everything below it goes, and of the entries EQUAL to it the first
+// `rank` in index order go too (rank = the select state's remaining rank = how many ties sort before the kept ones).  The
+// reference orders ties by an unstable QuickSort, i.e. arbitrarily; index order is the oracle's (stable) choice.
+template <typename T>
+__global__ void __launch_bounds__(256) k_biggest_apply(T *__restrict__ x, int64_t n, const SelBuf *__restrict__ sb) {
+    const T v = Key<T>::back(sb->st[0].prefix);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const T a = x[i] < 0 ? -x[i] : x[i];
+        if (a < v) x[i] = 0;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(1024) k_biggest_ties(T *__restrict__ x, int64_t n, const SelBuf *__restrict__ sb) {
+    // one CTA walks the array in index order and zeroes the first `rank` entries whose magnitude equals v (rare path)
+    __shared__ int wsum[32];
+    __shared__ long long base_s;
+    const long long todo = sb->st[0].rank;
+    if (todo <= 0) return;
+    const T v = Key<T>::back(sb->st[0].prefix);
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < n; c0 += blockDim.x) {
+        const int64_t i = c0 + threadIdx.x;
+        int tie = 0;
+        if (i < n) { const T a = x[i] < 0 ? -x[i] : x[i]; tie = (a == v) ? 1 : 0; }
+        int incl = tie;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
+        const long long ord = base_s + woff + incl - tie;                  // ties before this entry
+        if (tie && ord < todo) x[i] = 0;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) base_s += woff + incl;
+        __syncthreads();
+        if (base_s >= todo) break;
+    }
+}
+
 static unsigned grid_for_n(int64_t n) {
     int64_t b = (n + 255) / 256;
     if (b < 1) b = 1;
@@ -187,7 +228,7 @@ static bool device_mad(T *v, int64_t m, SelBuf *sb, T *med, double *sigma_dev, c
             k_sel_init<<<1, 256, 0, st>>>(sb, (long long)((m - 1) / 2), (long long)(m / 2));
         }
         for (int shift = Key<T>::BITS - 8; shift >= 0; shift -= 8) {
-            { LaunchScope scope("select_hist", st); k_sel_hist<T><<<g, 256, 0, st>>>(v, m, sb, shift); }
+            { LaunchScope scope("select_hist", st); k_sel_hist<T, false><<<g, 256, 0, st>>>(v, m, sb, shift); }
             { LaunchScope scope("select_pick", st); k_sel_pick<<<1, 256, 0, st>>>(sb, shift); }
         }
         { LaunchScope scope("select_finish", st); k_sel_finish<T><<<1, 32, 0, st>>>(sb, med, sigma_dev, round); }
@@ -318,6 +359,37 @@ extern "C" int32_t wb200_threshold(void *x, int64_t count, int32_t kind, double 
         else                    k_threshold<float><<<grid_for_n(count), 256, 0, st>>>((float *)x, count, kind, t, nullptr, 1.0);
     }
     return check_launch("threshold") ? WB200_OK : WB200_ECUDA;
+}
+
+extern "C" int32_t wb200_threshold_biggest(void *x, int64_t count, int64_t m, int32_t dtype, void *stream) {
+    if (dtype != WB200_F32 && dtype != WB200_F64) { set_error("threshold supports Float32/Float64"); return WB200_EDTYPE; }
+    if (count < 0 || (count > 0 && x == nullptr) || m < 0) { set_error("bad argument (m >= 0)"); return WB200_EARG; }   // @assert m >= 0
+    if (count == 0 || m >= count) return WB200_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t esz = dtype == WB200_F64 ? 8 : 4;
+    if (m == 0) return cudaMemsetAsync(x, 0, (size_t)count * esz, st) == cudaSuccess ? WB200_OK : WB200_ECUDA;
+    SelBuf *sb = nullptr;
+    keep_pool_memory();
+    if (cudaMallocAsync((void **)&sb, sizeof(SelBuf), st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(select state) failed"); return WB200_ECUDA; }
+    const unsigned g = grid_for_n(count);
+    const long long k = (long long)(count - m);
+    { LaunchScope scope("select_init", st); k_sel_init<<<1, 256, 0, st>>>(sb, k, k); }
+    for (int shift = (int)esz * 8 - 8; shift >= 0; shift -= 8) {
+        {
+            LaunchScope scope("select_hist", st);
+            if (dtype == WB200_F64) k_sel_hist<double, true><<<g, 256, 0, st>>>((const double *)x, count, sb, shift);
+            else                    k_sel_hist<float, true><<<g, 256, 0, st>>>((const float *)x, count, sb, shift);
+        }
+        { LaunchScope scope("select_pick", st); k_sel_pick<<<1, 256, 0, st>>>(sb, shift); }
+    }
+    {
+        LaunchScope scope("biggest_apply", st);
+        if (dtype == WB200_F64) { k_biggest_ties<double><<<1, 1024, 0, st>>>((double *)x, count, sb); k_biggest_apply<double><<<g, 256, 0, st>>>((double *)x, count, sb); }
+        else                    { k_biggest_ties<float><<<1, 1024, 0, st>>>((float *)x, count, sb); k_biggest_apply<float><<<g, 256, 0, st>>>((float *)x, count, sb); }
+    }
+    const bool ok = check_launch("threshold_biggest");
+    cudaFreeAsync(sb, st);
+    return ok ? WB200_OK : WB200_ECUDA;
 }
 
 extern "C" int32_t wb200_noisest(double *sigma_out, const void *x, int32_t ndim, const int64_t *dims, int32_t wkind,

@@ -3,7 +3,7 @@ denoising.jl): threshold types, `threshold` / `threshold_` (threshold!), `VisuSh
 
 Everything runs through the C ABI (`wb200_threshold`, `wb200_noisest`, `wb200_denoise`) on CUDA tensors; there is no CPU
 path.  `denoise` is a pure enqueue: with the default `estnoise` the noise level is estimated on the device and never
-visits the host.  Not on the device path yet: `BiggestTH` (m-term approximation; needs an ordered selection),
+visits the host.  `BiggestTH` (m-term approximation) uses the same radix select as the noise estimate.  Not on the device path:
 `matchingpursuit`, `bestbasistree`, entropy (SURVEY 8f rows 3+).
 """
 from __future__ import annotations
@@ -52,10 +52,22 @@ def _real(x):
 
 def threshold_(x, TH: THType, t=None):
     """threshold!(x, TH, t) / threshold!(x, TH) in place (threshold_main.jl:35-117)."""
-    if isinstance(TH, BiggestTH):
-        raise NotImplementedError("BiggestTH (m-term approximation) is not on the device path yet")
     if not isinstance(TH, THType):
         raise TypeError("TH must be a threshold type (HardTH(), SoftTH(), ...)")
+    if isinstance(TH, BiggestTH):           # threshold!(x, BiggestTH(), m::Int): the m-term approximation
+        if t is None or int(t) != t:
+            raise TypeError("BiggestTH takes an integer number of terms m")
+        if int(t) < 0:
+            raise AssertionError("m >= 0")
+        if not isinstance(x, torch.Tensor) or not x.is_cuda or x.dtype not in (torch.float32, torch.float64):
+            raise TypeError("threshold_ operates in place on a Float32 / Float64 CUDA tensor")
+        if x.numel():
+            if not (x.is_contiguous() or _is_colmajor(x)):
+                raise TypeError("threshold_ needs dense storage")
+            with torch.cuda.device(x.device):
+                rc = _lib.lib().wb200_threshold_biggest(x.data_ptr(), x.numel(), int(t), _DTYPES[x.dtype], _stream(x))
+            _check(rc)
+        return x
     if isinstance(TH, (NegTH, PosTH)):
         if t is not None:
             raise TypeError(f"{TH!r} takes no threshold value")
@@ -144,8 +156,8 @@ def denoise(x, wt=DEFAULT_WAVELET, L=None, dnt=None, estnoise=None, TI: bool = F
         dnt = VisuShrink(int(x.shape[0]))
     if not isinstance(dnt, VisuShrink):
         raise TypeError("dnt must be a VisuShrink")
-    if isinstance(dnt.th, BiggestTH):
-        raise NotImplementedError("BiggestTH (m-term approximation) is not on the device path yet")
+    if isinstance(dnt.th, BiggestTH):       # threshold!(xt, BiggestTH(), sigma * t) has no method upstream either (m::Int)
+        raise TypeError("VisuShrink needs a value threshold type; BiggestTH takes a term count")
     if nspin is None:
         nspin = tuple(8 for _ in range(x.dim()))
     sp = [int(nspin)] if isinstance(nspin, (int, np.integer)) else [int(v) for v in nspin]
