@@ -149,6 +149,16 @@ int32_t wb200_denoise(void *y, const void *x, int32_t ndim, const int64_t *dims,
                       int32_t th_kind, double tfac, double sigma, int32_t TI, const int32_t *nspin, int32_t dtype,
                       void *stream, uint32_t flags);
 
+/* ---- best basis: coefentropy / bestbasistree, src/Threshold/entropy.jl:16-129 ----
+ * et 0: ShannonEntropy, 1: LogEnergyEntropy.  coefentropy: nrm = NaN means norm(x).  bestbasistree: y on the device (n samples),
+ * tree / besttree host byte arrays (2^Lmax - 1 nodes, heap order); entr_bf (ntree) / entr_af (2^(Lmax-1)) optional host outputs
+ * of the entropy tables.  Both return host values and therefore wait for the stream. */
+int32_t wb200_coefentropy(double *out, const void *x, int64_t count, int32_t et, double nrm, int32_t dtype, void *stream);
+int32_t wb200_bestbasistree(uint8_t *besttree, double *entr_bf, double *entr_af, const void *y, int64_t n, int32_t wkind,
+                            const double *qmf, int32_t flen, const wb200_lift_step *steps, int32_t nsteps, double norm1,
+                            double norm2, const uint8_t *tree, int64_t ntree, int32_t et, int32_t dtype, void *stream,
+                            uint32_t flags);
+
 /* ---- host-buffer forms (end-to-end path): x_host / y_host are HOST pointers (pinned memory gives full
  * PCIe bandwidth).  The batch is cut into chunks that are copied in, transformed and copied out on
  * alternating streams so the three stages overlap; the call returns after the last chunk has landed

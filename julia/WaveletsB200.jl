@@ -163,6 +163,28 @@ function Wavelets.Threshold.denoise(x::CuArray{T,N}, wt::Union{DiscreteWavelet,N
     check(rc); y
 end
 
+# ---- best basis: coefentropy / bestbasistree (src/Threshold/entropy.jl) -------------------------------------------------
+et_code(::Wavelets.Threshold.ShannonEntropy) = Int32(0); et_code(::Wavelets.Threshold.LogEnergyEntropy) = Int32(1)
+function Wavelets.Threshold.coefentropy(x::CuArray{T}, et::Wavelets.Threshold.Entropy, nrm::T=T(NaN)) where {T<:Union{Float32,Float64}}
+    out = Ref{Float64}(0)
+    rc = ccall((:wb200_coefentropy, LIB), Int32, (Ptr{Float64}, CuPtr{Cvoid}, Int64, Int32, Float64, Int32, Ptr{Cvoid}),
+               out, pointer(x), length(x), et_code(et), Float64(nrm), dtype_code(T), CUDA.stream().handle)
+    check(rc); T(out[])
+end
+function Wavelets.Threshold.bestbasistree(y::CuVector{T}, wt::DiscreteWavelet, tree::BitVector,
+                                          et::Wavelets.Threshold.Entropy=Wavelets.Threshold.ShannonEntropy()) where {T<:Union{Float32,Float64}}
+    wk, qmf, steps, n1, n2 = wt_args(wt); t = Vector{UInt8}(tree); best = similar(t)
+    rc = ccall((:wb200_bestbasistree, LIB), Int32,
+               (Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}, CuPtr{Cvoid}, Int64, Int32, Ptr{Float64}, Int32, Ptr{LiftStep}, Int32, Float64, Float64,
+                Ptr{UInt8}, Int64, Int32, Int32, Ptr{Cvoid}, UInt32),
+               best, C_NULL, C_NULL, pointer(y), length(y), wk, qmf, length(qmf), steps, length(steps), n1, n2, t, length(t), et_code(et),
+               dtype_code(T), CUDA.stream().handle, flags())
+    check(rc); BitVector(best .!= 0)
+end
+Wavelets.Threshold.bestbasistree(y::CuVector{T}, wt::DiscreteWavelet, L::Integer=maxtransformlevels(y),
+                                 et::Wavelets.Threshold.Entropy=Wavelets.Threshold.ShannonEntropy()) where {T<:Union{Float32,Float64}} =
+    Wavelets.Threshold.bestbasistree(y, wt, maketree(length(y), L, :full), et)
+
 # ---- column-wise batch forms (the last dimension indexes independent signals / images) ---------------------------
 export dwtc, idwtc
 dwtc(x::CuArray, wt::OrthoFilter, L::Integer=minimum(maxtransformlevels.(size(x)[1:end-1]))) =

@@ -274,3 +274,36 @@ def denoise(x, wt, L, kind="hard", tfac=None, sigma=None, TI=False, nspin=8):
                                              C.c_double(float("nan") if sigma is None else float(sigma)), C.c_int(1 if TI else 0), spin)
     _check(rc)
     return y
+
+
+# ---- best basis ---------------------------------------------------------------------------------
+ET_KINDS = {"shannon": 0, "logenergy": 1}
+
+
+def coefentropy(x, et="shannon", nrm=None):
+    x = np.ascontiguousarray(x)
+    sfx, ct = _sfx(x.dtype)
+    if nrm is None:
+        nrm = np.sqrt(np.sum(x.astype(np.float64) ** 2))
+    f = getattr(lib(), "orc_coefentropy" + sfx)
+    f.restype = ct
+    return float(f(x.ctypes.data_as(C.c_void_p), C.c_int64(x.size), C.c_int(ET_KINDS[et]), ct(float(nrm))))
+
+
+def bestbasistree(y, wt, tree, et="shannon"):
+    """Reference `bestbasistree(y, wt, tree, et)` -> (besttree uint8, entr_bf, entr_af)."""
+    y = np.ascontiguousarray(y)
+    sfx, ct = _sfx(y.dtype)
+    n = y.shape[0]
+    t = np.ascontiguousarray(tree, dtype=np.uint8)
+    best = t.copy()
+    Lmax = maxtransformlevels(n)
+    bf = np.zeros(len(t), dtype=y.dtype)
+    af = np.zeros(1 << max(Lmax - 1, 0), dtype=y.dtype)
+    wk, qp, fl, st, ns, n1, n2, keep = _wt_args(wt)
+    rc = getattr(lib(), "orc_bestbasistree" + sfx)(best.ctypes.data_as(C.c_void_p), bf.ctypes.data_as(C.c_void_p), af.ctypes.data_as(C.c_void_p),
+                                                   y.ctypes.data_as(C.c_void_p), C.c_int64(n), C.c_int(wk), qp, C.c_int(fl), st, C.c_int(ns),
+                                                   C.c_double(n1), C.c_double(n2), t.ctypes.data_as(C.c_void_p), C.c_int64(len(t)),
+                                                   C.c_int(ET_KINDS[et]))
+    _check(rc)
+    return best, bf, af

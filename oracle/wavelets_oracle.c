@@ -150,7 +150,9 @@ static void getliftranges(int64_t half, int nc, int64_t shift, int is_predict,
 #undef FN
 
 #define T float
+#define ORC_IS_F32 1
 #define FN(name) CAT(name, _f32)
 #include "oracle_impl.inc"
 #undef T
 #undef FN
+#undef ORC_IS_F32

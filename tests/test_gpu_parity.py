@@ -844,3 +844,55 @@ def test_threshold_biggest_vs_oracle(dev, dtype):
     assert torch.equal(yb, torch.where(kept, xb, torch.zeros_like(xb)))
     with pytest.raises(TypeError):
         wb.threshold(xb, wb.BiggestTH(), 2.5)
+
+
+# ------------------------------------------------------------------------------------------------------
+# best basis (src/Threshold/entropy.jl).  Entropies agree to rounding (device sums are ordered differently and
+# accumulated in double), trees are compared on signals without near-ties.
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_coefentropy_and_bestbasistree(dev, dtype):
+    wt, wl = wavelet(WT.db4), wavelet(WT.cdf97, WT.Lifting)
+    rel = 1e-11 if dtype == np.float64 else 2e-3      # (the Float32 reference sums thousands of terms sequentially in Float32)
+    v = rng(3).standard_normal(5000).astype(dtype)
+    for et, name in ((wb.ShannonEntropy(), "shannon"), (wb.LogEnergyEntropy(), "logenergy")):
+        ref = orc.coefentropy(v, name)
+        assert abs(wb.coefentropy(to_gpu(v, dev), et) - ref) <= rel * abs(ref)
+        ref2 = orc.coefentropy(v, name, 3.0)
+        assert abs(wb.coefentropy(to_gpu(v, dev), et, 3.0) - ref2) <= rel * abs(ref2)
+    assert wb.coefentropy(to_gpu(np.zeros(16, dtype=dtype), dev)) == 0.0
+    for n in (1024, 5 * 64, 4096):                                                # the reference's two test signals + a longer one
+        x = np.sin(4 * np.linspace(0, 2 * np.pi - np.finfo(float).eps, n)).astype(dtype)
+        x = x + (0.01 * rng(n).standard_normal(n)).astype(dtype)
+        for w_, name in ((wt, "shannon"), (wl, "shannon"), (wt, "logenergy")):
+            et = wb.ShannonEntropy() if name == "shannon" else wb.LogEnergyEntropy()
+            full = wb.maketree(n, None, "full")
+            rb, rbf, raf = orc.bestbasistree(x, w_, full, name)
+            tree, bf, af = wb.bestbasistree(to_gpu(x, dev), w_, None, et, return_entropies=True)
+            # -log(s) is ill-conditioned for small coefficients: in Float32 the reference itself moves by 3e-3 between Float32 and
+            # Float64 arithmetic on the same data (581.65 vs 579.99 for a node of the 4096-sample signal)
+            tol = rel if dtype == np.float64 else (1e-5 if name == "shannon" else 1e-2)
+            assert np.max(np.abs(bf - rbf) / np.maximum(1.0, np.abs(rbf))) <= tol and np.max(np.abs(af - raf) / np.maximum(1.0, np.abs(raf))) <= tol
+            assert wb.isvalidtree(n, tree)
+            if dtype == np.float64:
+                assert np.array_equal(tree, rb), (n, name)
+            xtb = wb.wpt(to_gpu(x, dev), w_, tree)                                # test/threshold.jl:27-29
+            assert float((wb.iwpt(xtb, w_, tree) - to_gpu(x, dev)).abs().max()) < (1e-10 if dtype == np.float64 else 1e-4)
+    # a restricted input tree, an invalid tree
+    x = to_gpu(rng(1).standard_normal(256).astype(dtype), dev)
+    t2 = wb.bestbasistree(x, wt, 3)
+    assert not np.any(t2.astype(bool) & ~wb.maketree(256, 3, "full").astype(bool))
+    with pytest.raises(wb.ArgumentError, match="invalid tree"):
+        wb.bestbasistree(x, wt, np.ones(7, dtype=np.uint8))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_lifting_many_tiny_lines(dev, mode, dtype):
+    """thousands of 2- and 4-sample lines in one call (the nodes of a deep packet level): the generic lifting tile must
+    stay within the default shared-memory limit"""
+    wl = wavelet(WT.cdf97, WT.Lifting)
+    for n, B in ((2, 5000), (4, 3000), (8, 2048)):
+        x = rng(n + B).standard_normal((n, B)).astype(dtype)
+        y = wb.dwtc(to_gpu(x, dev), wl, 1)
+        check(y, orc.dwt_lifting_batch(x, 1, wl.step, wl.norm1, wl.norm2, 1), mode, 1, 4.0)
+        check(wb.idwtc(y, wl, 1), orc.dwt_lifting_batch(to_np(y), 1, wl.step, wl.norm1, wl.norm2, 1, fw=False), mode, 1, 4.0)

@@ -304,3 +304,34 @@ def test_threshold_biggest_definition():
             ref[np.argsort(np.abs(x), kind="stable")[: max(0, len(x) - m)]] = 0
             assert np.array_equal(orc.threshold_biggest(x, m), ref)
             assert np.count_nonzero(orc.threshold_biggest(x, m)) <= m
+
+
+# ------------------------------------------------------------------------------------------------------
+# best basis (src/Threshold/entropy.jl; the reference's own checks: test/threshold.jl:24-35)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1024, 5 * 64])
+def test_bestbasistree_reference_relations(n):
+    wt = wavelet(WT.db4)
+    x = np.sin(4 * np.linspace(0, 2 * np.pi - np.finfo(float).eps, n))
+    full = wb.maketree(n, None, "full")
+    best, bf, af = orc.bestbasistree(x, wt, full)
+    assert wb.isvalidtree(x, best)
+    xtb = orc.wpt_filter(x, wt.qmf, best)
+    assert np.allclose(orc.wpt_filter(xtb, wt.qmf, best, fw=False), x, rtol=0, atol=1e-12)      # iwpt(wpt(x, tree), tree) ~ x
+    # the chosen basis costs no more than the signal itself, the dwt basis or the full tree (additive cost, same norm)
+    nrm = np.linalg.norm(x)
+    cost = lambda c: orc.coefentropy(c, "shannon", nrm)
+    cb = cost(xtb)
+    assert cb <= cost(x) + 1e-12 and cb <= cost(orc.wpt_filter(x, wt.qmf, wb.maketree(n, None, "dwt"))) + 1e-12
+    assert cb <= cost(orc.wpt_filter(x, wt.qmf, full)) + 1e-12
+    # entr_bf[0] is the entropy of the signal; a restricted input tree bounds the result
+    assert abs(bf[0] - cost(x)) <= 1e-12 * max(1.0, abs(bf[0]))
+    small = wb.maketree(n, 2, "full")
+    b2, _, _ = orc.bestbasistree(x, wt, small)
+    assert not np.any(b2 & ~small.astype(bool))
+    # definitions
+    v = rng(3).standard_normal(50)
+    s = (v / np.linalg.norm(v)) ** 2
+    assert abs(orc.coefentropy(v, "shannon") - np.sum(-s * np.log(s))) <= 1e-12
+    assert abs(orc.coefentropy(v, "logenergy") - np.sum(-np.log(s))) <= 1e-10
+    assert orc.coefentropy(np.zeros(8), "shannon") == 0.0

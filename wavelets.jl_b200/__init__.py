@@ -16,10 +16,11 @@ from .util import maxtransformlevels, maketree, isvalidtree, detailindex, detail
 from .transforms import (modwt, imodwt, maxmodwttransformlevels, dwt, idwt, dwt_, idwt_, wpt, iwpt, wpt_, iwpt_, dwtc, idwtc, dwt_oop_, idwt_oop_,
                          ArgumentError, DimensionMismatch, set_strict_fp, colmajor)
 from . import threshold as Threshold
-from .threshold import (HardTH, SoftTH, SemiSoftTH, SteinTH, BiggestTH, PosTH, NegTH, threshold, threshold_, VisuShrink, denoise, noisest)
+from .threshold import (HardTH, SoftTH, SemiSoftTH, SteinTH, BiggestTH, PosTH, NegTH, threshold, threshold_, VisuShrink, denoise, noisest,
+                        ShannonEntropy, LogEnergyEntropy, coefentropy, bestbasistree)
 
 __all__ = ["modwt", "imodwt", "maxmodwttransformlevels", "WT", "Util", "wavelet", "maxtransformlevels", "maketree", "isvalidtree", "detailindex",
            "detailrange", "detailn", "dwt", "idwt", "dwt_", "idwt_", "wpt", "iwpt", "wpt_", "iwpt_",
            "dwtc", "idwtc", "dwt_oop_", "idwt_oop_", "ArgumentError", "DimensionMismatch",
            "set_strict_fp", "colmajor", "Threshold", "HardTH", "SoftTH", "SemiSoftTH", "SteinTH", "BiggestTH", "PosTH", "NegTH",
-           "threshold", "threshold_", "VisuShrink", "denoise", "noisest"]
+           "threshold", "threshold_", "VisuShrink", "denoise", "noisest", "ShannonEntropy", "LogEnergyEntropy", "coefentropy", "bestbasistree"]

@@ -29,7 +29,7 @@ SYMBOLS = [
     "wb200_last_error_string", "wb200_version", "wb200_launch_count",
     "wb200_profile_enable", "wb200_profile_collect",
     "wb200_modwt", "wb200_imodwt", "wb200_maxmodwttransformlevels",
-    "wb200_threshold", "wb200_threshold_biggest", "wb200_noisest", "wb200_denoise",
+    "wb200_threshold", "wb200_threshold_biggest", "wb200_noisest", "wb200_denoise", "wb200_coefentropy", "wb200_bestbasistree",
 ]
 
 
@@ -73,6 +73,10 @@ def lib() -> C.CDLL:
     L.wb200_denoise.argtypes = [vp, vp, i32, C.POINTER(i64), i32, pd, i32, C.POINTER(LiftStep), i32, C.c_double, C.c_double, i32,
                                 i32, C.c_double, C.c_double, i32, C.POINTER(i32), i32, vp, u32]
     L.wb200_denoise.restype = i32
+    L.wb200_coefentropy.argtypes = [pd, vp, i64, i32, dbl, i32, vp]
+    L.wb200_coefentropy.restype = i32
+    L.wb200_bestbasistree.argtypes = [pu8, pd, pd, vp, i64, i32, pd, i32, pst, i32, dbl, dbl, pu8, i64, i32, i32, vp, u32]
+    L.wb200_bestbasistree.restype = i32
     L.wb200_workspace_bytes.argtypes = [i32, i32, p64, i64, i32, i32, u32]
     L.wb200_workspace_bytes.restype = sz
     L.wb200_maxtransformlevels.argtypes = [i64]

@@ -432,6 +432,10 @@ static bool plan_lift_tile(const Extent &e, const LiftScheme<T> &sc, bool kfast,
         if (half <= 1024 && half <= cap) {
             t.whole = 1; t.W = (int)half; t.tp = (int)half;
             int64_t tl = 1024 / half; if (tl < 1) tl = 1; if (tl > NL) tl = NL; if (tl * half > cap) tl = cap / half;
+            // very short lines: the per-line bookkeeping (36 bytes) outweighs the samples -- keep the CTA within the default
+            // 48 KB of dynamic shared memory (1024 lines of 2 samples asked for 53 KB: launch failure)
+            const int64_t per_line_bytes = 2 * half * (int64_t)sizeof(T) + 4 * (int64_t)sizeof(int64_t) + (int64_t)sizeof(int);
+            if (tl * per_line_bytes > 40 * 1024) tl = (40 * 1024) / per_line_bytes;
             t.tln = (int)(tl < 1 ? 1 : tl);
         } else {
             t.whole = 0; t.tln = 1; t.tp = 1024 - halo; if (t.tp > cap - halo) t.tp = cap - halo;

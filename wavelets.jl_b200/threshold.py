@@ -16,11 +16,11 @@ import torch
 
 from . import _lib
 from .transforms import ArgumentError, _check, _colmajor_strides, _DTYPES, _flags_value, _is_colmajor, _prep, _stream
-from .util import iscube, maxtransformlevels
+from .util import iscube, isvalidtree, maketree, maxtransformlevels
 from . import wt as WT
 from .wt import GLS, OrthoFilter, wavelet
 
-__all__ = ["THType", "HardTH", "SoftTH", "SemiSoftTH", "SteinTH", "BiggestTH", "PosTH", "NegTH", "DEFAULT_TH",
+__all__ = ["Entropy", "ShannonEntropy", "LogEnergyEntropy", "coefentropy", "bestbasistree", "THType", "HardTH", "SoftTH", "SemiSoftTH", "SteinTH", "BiggestTH", "PosTH", "NegTH", "DEFAULT_TH",
            "threshold", "threshold_", "DNFT", "VisuShrink", "denoise", "noisest", "DEFAULT_WAVELET"]
 
 
@@ -177,3 +177,64 @@ def denoise(x, wt=DEFAULT_WAVELET, L=None, dnt=None, estnoise=None, TI: bool = F
                                           _flags_value())
         _check(rc)
     return y
+
+
+# ---- entropy / best basis (src/Threshold/entropy.jl) ----------------------------------------------------------------
+class Entropy:
+    kind = None
+
+    def __repr__(self):
+        return type(self).__name__ + "()"
+
+
+class ShannonEntropy(Entropy): kind = 0       # Coifman-Wickerhauser
+class LogEnergyEntropy(Entropy): kind = 1
+
+
+def coefentropy(x, et: Entropy = None, nrm=None) -> float:
+    """coefentropy(x, et, nrm = norm(x)): the additive entropy of the coefficients (entropy.jl:16-43)."""
+    et = ShannonEntropy() if et is None else et
+    if not isinstance(et, Entropy):
+        raise TypeError("et must be ShannonEntropy() or LogEnergyEntropy()")
+    x = _real(x)
+    if nrm is not None and not float(nrm) >= 0:
+        raise AssertionError("nrm >= 0")
+    out = C.c_double(0.0)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().wb200_coefentropy(C.byref(out), x.data_ptr(), x.numel(), et.kind, float("nan") if nrm is None else float(nrm),
+                                          _DTYPES[x.dtype], _stream(x))
+    _check(rc)
+    return out.value
+
+
+def bestbasistree(y, wt, L=None, et: Entropy = None, return_entropies: bool = False):
+    """bestbasistree(y, wt, L = maxtransformlevels(y), et = ShannonEntropy()) / bestbasistree(y, wt, tree, et): the best
+    packet tree that is a subset of the input tree (entropy.jl:46-108).  Returns the tree as the uint8 array `maketree` gives
+    (usable with `wpt` / `iwpt`)."""
+    et = ShannonEntropy() if et is None else et
+    if not isinstance(et, Entropy):
+        raise TypeError("et must be ShannonEntropy() or LogEnergyEntropy()")
+    y = _real(y)
+    if y.dim() != 1:
+        raise TypeError("bestbasistree takes a vector")
+    n = int(y.shape[0])
+    if L is None or isinstance(L, (int, np.integer)):
+        tree = maketree(n, L, "full")
+    else:
+        tree = np.ascontiguousarray(np.asarray(L), dtype=np.uint8)
+    if not isvalidtree(n, tree):
+        raise ArgumentError("invalid tree")
+    if wt is None:
+        raise TypeError("bestbasistree needs a wavelet")
+    wk, qp, fl, st, ns, n1, n2, keep = _wt_args(wt)
+    Lmax = maxtransformlevels(n)
+    best = np.zeros(len(tree), dtype=np.uint8)
+    bf = np.zeros(len(tree), dtype=np.float64)
+    af = np.zeros(1 << max(Lmax - 1, 0), dtype=np.float64)
+    pu8, pd = C.POINTER(C.c_uint8), C.POINTER(C.c_double)
+    with torch.cuda.device(y.device):
+        rc = _lib.lib().wb200_bestbasistree(best.ctypes.data_as(pu8), bf.ctypes.data_as(pd), af.ctypes.data_as(pd), y.data_ptr(), n, wk, qp,
+                                            fl, st, ns, n1, n2, tree.ctypes.data_as(pu8), len(tree), et.kind, _DTYPES[y.dtype], _stream(y),
+                                            _flags_value())
+    _check(rc)
+    return (best, bf, af) if return_entropies else best
