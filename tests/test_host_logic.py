@@ -116,3 +116,52 @@ def test_shard_ranges():
     assert [shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
     assert shard_range(1024, 7, 8) == (896, 1024)
     assert sum(shard_sizes(5, 8)) == 5
+
+
+def test_widened_entry_points_argument_checks_without_gpu():
+    """MODWT / threshold / denoise / best-basis entry points validate before any CUDA call (status codes carry the
+    reference's messages: transforms_maximal_overlap.jl:46-48, denoising.jl:30, entropy.jl:52)."""
+    L = _lib.lib()
+    q = np.ascontiguousarray(wavelet(WT.db4).qmf)
+    qp = q.ctypes.data_as(C.POINTER(C.c_double))
+    fx, fy = 0x1000, 0x2000
+    assert L.wb200_modwt(fy, fx, 129, 1, qp, 8, 8, _lib.F64, None, 0, None, 0) == _lib.ELEVEL
+    assert b"Too many transform levels" in L.wb200_last_error_string()
+    assert L.wb200_modwt(fy, fx, 129, 1, qp, 8, 0, _lib.F64, None, 0, None, 0) == _lib.ELEVEL
+    assert b"L must be >= 1" in L.wb200_last_error_string()
+    assert L.wb200_modwt(fy, fx, 129, 1, qp, 8, 3, _lib.C64, None, 0, None, 0) == _lib.EDTYPE
+    assert L.wb200_maxmodwttransformlevels(129) == 7 and L.wb200_maxmodwttransformlevels(128) == 7
+    assert L.wb200_threshold(fx, 10, 9, 1.0, _lib.F32, None) == _lib.EARG
+    assert L.wb200_threshold(fx, 10, 0, -1.0, _lib.F32, None) == _lib.EARG                      # @assert t >= 0
+    assert L.wb200_threshold(fx, 0, 0, 1.0, _lib.F32, None) == _lib.OK                          # empty array: nothing to do
+    assert L.wb200_threshold_biggest(fx, 10, -1, _lib.F32, None) == _lib.EARG                   # @assert m >= 0
+    assert L.wb200_threshold_biggest(fx, 10, 10, _lib.F32, None) == _lib.OK                     # m >= n keeps everything
+    spin = (C.c_int32 * 3)(8, 8, 1)
+    null_s = C.POINTER(_lib.LiftStep)()
+    nan = float("nan")
+    den = lambda dims, nd, wk, TI: L.wb200_denoise(fy, fx, nd, _lib.dims_array(dims), wk, qp, 8, null_s, 0, 0.0, 0.0, 2, 0, 3.0, nan,
+                                                   TI, spin, _lib.F32, None, 0)
+    assert den([16, 32], 2, 1, 0) == _lib.ENOTCUBE and b"square/cube" in L.wb200_last_error_string()
+    assert den([16], 1, 0, 1) == _lib.EARG and b"TI not supported" in L.wb200_last_error_string()
+    assert den([16], 1, 7, 0) == _lib.EARG
+    tree = np.array([0, 1, 0], dtype=np.uint8)
+    best = np.zeros(3, dtype=np.uint8)
+    pu8 = C.POINTER(C.c_uint8)
+    assert L.wb200_bestbasistree(best.ctypes.data_as(pu8), None, None, fx, 4, 1, qp, 8, null_s, 0, 0.0, 0.0, tree.ctypes.data_as(pu8), 3, 0,
+                                 _lib.F64, None, 0) == _lib.ETREE
+    out = C.c_double(1.0)
+    assert L.wb200_coefentropy(C.byref(out), fx, 0, 0, nan, _lib.F64, None) == _lib.OK and out.value == 0.0
+    assert L.wb200_coefentropy(C.byref(out), fx, 4, 5, nan, _lib.F64, None) == _lib.EARG
+
+
+def test_threshold_module_host_side():
+    assert abs(wb.VisuShrink(256).t - np.sqrt(2 * np.log(256))) < 1e-15 and isinstance(wb.VisuShrink(256).th, wb.HardTH)
+    assert wb.VisuShrink(wb.SoftTH(), 2.5).t == 2.5
+    assert len(wb.Threshold.DEFAULT_WAVELET.qmf) == 10                                           # sym5
+    assert [t.kind for t in (wb.HardTH(), wb.SoftTH(), wb.SemiSoftTH(), wb.SteinTH(), wb.NegTH(), wb.PosTH())] == [0, 1, 2, 3, 4, 5]
+    assert (wb.ShannonEntropy().kind, wb.LogEnergyEntropy().kind) == (0, 1)
+    for fn in (lambda: wb.threshold(torch.randn(8), wb.HardTH(), 1.0), lambda: wb.denoise(torch.randn(8)),
+               lambda: wb.noisest(torch.randn(8)), lambda: wb.coefentropy(torch.randn(8)),
+               lambda: wb.bestbasistree(torch.randn(8), wavelet(WT.db2)), lambda: wb.modwt(torch.randn(8), wavelet(WT.db2))):
+        with pytest.raises(TypeError, match="no CPU path"):
+            fn()
