@@ -335,3 +335,20 @@ def test_bestbasistree_reference_relations(n):
     assert abs(orc.coefentropy(v, "shannon") - np.sum(-s * np.log(s))) <= 1e-12
     assert abs(orc.coefentropy(v, "logenergy") - np.sum(-np.log(s))) <= 1e-10
     assert orc.coefentropy(np.zeros(8), "shannon") == 0.0
+
+
+def test_derived_regression_pins():
+    """tests/golden/derived_pins.json: this repository's own oracle outputs on a fixed input (MODWT, denoise, best basis) --
+    a regression guard for the restatement, not upstream data (see make_derived.py)."""
+    import json, os
+    pins = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "derived_pins.json")))
+    x = np.array(pins["x64"])
+    db4, sym5, cdf = wavelet(WT.db4), wavelet(WT.sym5), wavelet(WT.cdf97, WT.Lifting)
+    close = lambda a, b: np.allclose(np.asarray(a, dtype=np.float64).ravel(order="F"), np.asarray(b), rtol=0, atol=1e-13)
+    assert close(orc.modwt(x, np.asarray(db4.qmf), 3), pins["modwt_db4_L3"])
+    assert abs(orc.noisest(x, sym5) - pins["noisest_sym5"]) <= 1e-15
+    assert close(orc.denoise(x, sym5, 4), pins["denoise_sym5_L4"])
+    assert close(orc.denoise(x, sym5, 4, TI=True), pins["denoise_sym5_L4_TI"])
+    assert close(orc.denoise(x, cdf, 4, kind="soft", TI=True, nspin=4), pins["denoise_cdf97_soft_TI"])
+    best, bf, af = orc.bestbasistree(x, db4, wb.maketree(64, None, "full"))
+    assert best.tolist() == pins["bestbasis_db4_tree"] and close(bf, pins["bestbasis_db4_entr_bf"])
