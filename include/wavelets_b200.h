@@ -124,9 +124,9 @@ int32_t wb200_maxmodwttransformlevels(int64_t n);                             /*
 
 /* ---- thresholding and denoising: the main caller of the transforms, device end to end ----
  * threshold!(x, TH, t)            src/Threshold/threshold_main.jl:21-117
- * noisest(x, wt)                  src/Threshold/denoising.jl:88-106: level-1 transform, MAD of y[n1/2+1 : n1] (linear
- *                                 indices: the second half of the FIRST column, whatever ndim) over 0.6745.  Returns the
- *                                 number, so it waits for the stream.
+ * noisest(x, wt, L = 1)           src/Threshold/denoising.jl:88-106: y = dwt(x, wt, L), MAD of y[detailrange(y, L)] =
+ *                                 y[round(n1/2^L + 1) : round(n1/2^(L-1))] (LINEAR indices: a piece of the FIRST column,
+ *                                 whatever ndim) over 0.6745.  Returns the number, so it waits for the stream.
  * denoise(x, wt; L, dnt, TI, nspin)  denoising.jl:22-82, dnt = VisuShrink(th_kind, tfac): t = sigma * tfac.  Pure enqueue:
  *                                 sigma = NaN estimates the noise level on the device (noisest) and the threshold kernel
  *                                 reads it from device memory; a finite sigma is the caller's `estnoise` result.
@@ -143,7 +143,7 @@ int32_t wb200_threshold(void *x, int64_t count, int32_t kind, double t, int32_t 
 int32_t wb200_threshold_biggest(void *x, int64_t count, int64_t m, int32_t dtype, void *stream);
 int32_t wb200_noisest(double *sigma_out, const void *x, int32_t ndim, const int64_t *dims, int32_t wkind,
                       const double *qmf, int32_t flen, const wb200_lift_step *steps, int32_t nsteps, double norm1,
-                      double norm2, int32_t dtype, void *stream, uint32_t flags);
+                      double norm2, int32_t L, int32_t dtype, void *stream, uint32_t flags);
 int32_t wb200_denoise(void *y, const void *x, int32_t ndim, const int64_t *dims, int32_t wkind, const double *qmf,
                       int32_t flen, const wb200_lift_step *steps, int32_t nsteps, double norm1, double norm2, int32_t L,
                       int32_t th_kind, double tfac, double sigma, int32_t TI, const int32_t *nspin, int32_t dtype,
@@ -152,7 +152,10 @@ int32_t wb200_denoise(void *y, const void *x, int32_t ndim, const int64_t *dims,
 /* ---- best basis: coefentropy / bestbasistree, src/Threshold/entropy.jl:16-129 ----
  * et 0: ShannonEntropy, 1: LogEnergyEntropy.  coefentropy: nrm = NaN means norm(x).  bestbasistree: y on the device (n samples),
  * tree / besttree host byte arrays (2^Lmax - 1 nodes, heap order); entr_bf (ntree) / entr_af (2^(Lmax-1)) optional host outputs
- * of the entropy tables.  Both return host values and therefore wait for the stream. */
+ * of the entropy tables.  Both return host values and therefore wait for the stream.
+ * Ties: upstream keeps a node unsplit when `entr_bf[i] <= bestsubtree_entropy` (entropy.jl:97) on sums accumulated
+ * sequentially in T; the device sums are reduced in double in a different order, so the comparison carries a relative slack
+ * (1e-13 Float64, 1e-6 Float32) and a tie -- exact upstream, last-bit different here -- resolves as upstream: not split. */
 int32_t wb200_coefentropy(double *out, const void *x, int64_t count, int32_t et, double nrm, int32_t dtype, void *stream);
 int32_t wb200_bestbasistree(uint8_t *besttree, double *entr_bf, double *entr_af, const void *y, int64_t n, int32_t wkind,
                             const double *qmf, int32_t flen, const wb200_lift_step *steps, int32_t nsteps, double norm1,
@@ -193,6 +196,15 @@ int64_t wb200_launch_count(int32_t reset);
  * lines into buf (returns bytes written) and clears the record. */
 void wb200_profile_enable(int32_t on);
 int64_t wb200_profile_collect(char *buf, int64_t buflen);
+
+
+/* Scratch the library allocates itself (calls made with workspace == NULL) comes from a library-private
+ * stream-ordered memory pool of the current device, which keeps freed scratch for the next call (the reference
+ * re-allocates `si`, `snew`, `tmpbuffer` per call: src/Transforms/transforms_filter.jl:20-23; here that would be
+ * a re-map of up to gigabytes per call).  wb200_trim_pool releases everything above keep_bytes back to the
+ * device and returns the bytes the pool still reserves (-1 on error).  Callers that pass their own workspace
+ * never touch the pool. */
+int64_t wb200_trim_pool(int64_t keep_bytes);
 
 #ifdef __cplusplus
 }

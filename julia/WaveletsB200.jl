@@ -8,10 +8,10 @@
 module WaveletsB200
 
 using Wavelets
-using Wavelets.WT: OrthoFilter, GLS
+using Wavelets.WT: OrthoFilter, GLS, DiscreteWavelet
 using CUDA
 import Wavelets.Transforms: _dwt!, _wpt!
-import Wavelets.Util: maxtransformlevels, isvalidtree, sufficientpoweroftwo, iscube
+import Wavelets.Util: maxtransformlevels, maxmodwttransformlevels, isvalidtree, maketree, sufficientpoweroftwo, iscube
 
 const LIB = get(ENV, "WAVELETS_B200_LIB", "libwavelets_b200.so")
 
@@ -105,7 +105,7 @@ function _wpt!(y::CuVector{T}, scheme::GLS, tree::BitVector, fw::Bool) where T
 end
 
 # ---- maximal-overlap DWT: modwt(x, wt, L) / imodwt(xw, wt)  (transforms_maximal_overlap.jl:44-62, 98-108) ----------
-function Wavelets.modwt(x::CuVector{T}, wt::OrthoFilter, L::Integer=maxmodwttransformlevels(x)) where {T<:Union{Float32,Float64}}
+function Wavelets.Transforms.modwt(x::CuVector{T}, wt::OrthoFilter, L::Integer=maxmodwttransformlevels(x)) where {T<:Union{Float32,Float64}}
     L <= maxmodwttransformlevels(x) || throw(ArgumentError("Too many transform levels (length(x) < 2^L)"))
     L >= 1 || throw(ArgumentError("L must be >= 1"))
     qmf = Vector{Float64}(wt.qmf); y = CuArray{T}(undef, length(x), L + 1)
@@ -114,7 +114,7 @@ function Wavelets.modwt(x::CuVector{T}, wt::OrthoFilter, L::Integer=maxmodwttran
                pointer(y), pointer(x), length(x), 1, qmf, length(qmf), L, dtype_code(T), CU_NULL, 0, CUDA.stream().handle, flags())
     check(rc); y
 end
-function Wavelets.imodwt(xw::CuMatrix{T}, wt::OrthoFilter) where {T<:Union{Float32,Float64}}
+function Wavelets.Transforms.imodwt(xw::CuMatrix{T}, wt::OrthoFilter) where {T<:Union{Float32,Float64}}
     qmf = Vector{Float64}(wt.qmf); x = CuArray{T}(undef, size(xw, 1))
     rc = ccall((:wb200_imodwt, LIB), Int32,
                (CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Int64, Ptr{Float64}, Int32, Int32, Int32, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}, UInt32),
@@ -140,11 +140,11 @@ end
 wt_args(::Nothing) = (Int32(0), Float64[], LiftStep[], 0.0, 0.0)
 wt_args(f::OrthoFilter) = (Int32(1), Vector{Float64}(f.qmf), LiftStep[], 0.0, 0.0)
 wt_args(s::GLS) = (Int32(2), Float64[], LiftStep.(s.step), s.norm1, s.norm2)
-function Wavelets.Threshold.noisest(x::CuArray{T,N}, wt::Union{DiscreteWavelet,Nothing}=Wavelets.Threshold.DEFAULT_WAVELET) where {T<:Union{Float32,Float64},N}
+function Wavelets.Threshold.noisest(x::CuArray{T,N}, wt::Union{DiscreteWavelet,Nothing}=Wavelets.Threshold.DEFAULT_WAVELET, L::Integer=1) where {T<:Union{Float32,Float64},N}
     wk, qmf, steps, n1, n2 = wt_args(wt); out = Ref{Float64}(0)
     rc = ccall((:wb200_noisest, LIB), Int32,
-               (Ptr{Float64}, CuPtr{Cvoid}, Int32, Ptr{Int64}, Int32, Ptr{Float64}, Int32, Ptr{LiftStep}, Int32, Float64, Float64, Int32, Ptr{Cvoid}, UInt32),
-               out, pointer(x), N, dims3(x), wk, qmf, length(qmf), steps, length(steps), n1, n2, dtype_code(T), CUDA.stream().handle, flags())
+               (Ptr{Float64}, CuPtr{Cvoid}, Int32, Ptr{Int64}, Int32, Ptr{Float64}, Int32, Ptr{LiftStep}, Int32, Float64, Float64, Int32, Int32, Ptr{Cvoid}, UInt32),
+               out, pointer(x), N, dims3(x), wk, qmf, length(qmf), steps, length(steps), n1, n2, Int32(L), dtype_code(T), CUDA.stream().handle, flags())
     check(rc); out[]
 end
 function Wavelets.Threshold.denoise(x::CuArray{T,N}, wt::Union{DiscreteWavelet,Nothing}=Wavelets.Threshold.DEFAULT_WAVELET;

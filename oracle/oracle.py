@@ -247,13 +247,14 @@ def threshold_biggest(x, m):
     return y.reshape(np.shape(x), order="F")
 
 
-def noisest(x, wt):
+def noisest(x, wt, L=1):
+    """Reference `noisest(x, wt, L)` (denoising.jl:94-101)."""
     x = _fcopy(x)
     sfx, ct = _sfx(x.dtype)
     wk, qp, fl, st, ns, n1, n2, keep = _wt_args(wt)
     sig = C.c_double(0.0)
     rc = getattr(lib(), "orc_noisest" + sfx)(C.byref(sig), x.ctypes.data_as(C.c_void_p), C.c_int(x.ndim), _dims(x.shape), C.c_int(wk),
-                                             qp, C.c_int(fl), st, C.c_int(ns), C.c_double(n1), C.c_double(n2))
+                                             qp, C.c_int(fl), st, C.c_int(ns), C.c_double(n1), C.c_double(n2), C.c_int(int(L)))
     _check(rc)
     return sig.value
 

@@ -55,6 +55,8 @@ def test_util_helpers():
     assert wb.maketree(16, 3, "dwt").tolist() == [1, 1, 0, 1] + [0] * 11
     bad = np.zeros(15, dtype=np.uint8); bad[1] = 1
     assert not wb.isvalidtree(16, bad) and not wb.isvalidtree(16, np.ones(7))
+    # odd length: maxtransformlevels = 0, the only valid tree is the empty one (no TypeError from a fractional range)
+    assert wb.isvalidtree(7, np.zeros(0, dtype=np.uint8)) and not wb.isvalidtree(7, np.zeros(1, dtype=np.uint8))
 
 
 def test_colmajor_layout_helper():

@@ -178,6 +178,41 @@ def test_batch_driver_matches_loop():
 
 
 # ------------------------------------------------------------------------------------------------------
+# cdf 9/7 VALUES: upstream pins them with no vector -- only the step table (wt_main.jl:454-459) and
+# invertibility.  Independent known answer: the lifting steps are Daubechies & Sweldens' factorisation of the CDF 9/7
+# biorthogonal pair, so one analysis level must BE the published 9-tap / 7-tap analysis filters (12 printed digits, the
+# JPEG 2000 irreversible transform's table), with the reference's normalisation (norm1 = K, norm2 = 1/K) putting sqrt(2)
+# on the low-pass (DC gain sqrt(2): "constant in -> approx sqrt(2), details 0") and 1/sqrt(2) on the high-pass.
+# ------------------------------------------------------------------------------------------------------
+CDF97_LP = [0.026748757411, -0.016864118443, -0.078223266529, 0.266864118443, 0.602949018236,
+            0.266864118443, -0.078223266529, -0.016864118443, 0.026748757411]
+CDF97_HP = [0.091271763114, -0.057543526229, -0.591271763114, 1.115087052457,
+            -0.591271763114, -0.057543526229, 0.091271763114]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_cdf97_lifting_equals_published_filter_bank(dtype):
+    wl = wavelet(WT.cdf97, WT.Lifting)
+    n = 64
+    x = rng(97).standard_normal(n).astype(dtype)
+    y = orc.dwt_lifting(x, wl.step, wl.norm1, wl.norm2, 1).astype(np.float64)
+    lp, hp = np.sqrt(2) * np.array(CDF97_LP), np.array(CDF97_HP) / np.sqrt(2)
+    xd = x.astype(np.float64)
+    k = np.arange(n // 2)
+    s = sum(lp[m] * xd[(2 * k + m - 4) % n] for m in range(9))          # low-pass centred on the even sample 2k
+    d = sum(hp[m] * xd[(2 * k + 1 + m - 3) % n] for m in range(7))      # high-pass centred on the odd sample 2k+1
+    tol = 2e-11 if dtype == np.float64 else 2e-6                        # 12 published digits / Float32 rounding
+    assert np.max(np.abs(y[: n // 2] - s)) <= tol and np.max(np.abs(y[n // 2:] - d)) <= tol
+    # two levels: the second acts on the first level's approximation in exactly the same way
+    y2 = orc.dwt_lifting(x, wl.step, wl.norm1, wl.norm2, 2).astype(np.float64)
+    k2 = np.arange(n // 4)
+    s2 = sum(lp[m] * s[(2 * k2 + m - 4) % (n // 2)] for m in range(9))
+    d2 = sum(hp[m] * s[(2 * k2 + 1 + m - 3) % (n // 2)] for m in range(7))
+    assert np.max(np.abs(y2[: n // 4] - s2)) <= 2 * tol and np.max(np.abs(y2[n // 4: n // 2] - d2)) <= 2 * tol
+    assert np.max(np.abs(y2[n // 2:] - d)) <= tol
+
+
+# ------------------------------------------------------------------------------------------------------
 # MODWT: the reference holds no golden vector for it, only relations (test/transforms.jl:325-344).
 # Those, plus a pin onto the golden-checked decimated transform: the level-1 MODWT bands, decimated and scaled by
 # sqrt(2), are the level-1 DWT bands.
@@ -212,6 +247,40 @@ def test_modwt_level1_is_undecimated_dwt(wname):
     k = np.arange(n // 2)
     assert np.allclose(np.sqrt(2) * W[(2 * k + F - 1) % n, 1], y[: n // 2], rtol=0, atol=1e-13)
     assert np.allclose(np.sqrt(2) * W[(2 * k + 1) % n, 0], y[n // 2:], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("wname", ["haar", "db4", "sym8"])
+@pytest.mark.parametrize("n", [128, 129, 1000])
+def test_modwt_all_levels_vs_independent_fft_statement(wname, n):
+    """Pins the oracle's MODWT at EVERY level (not only level 1) to an independent statement that shares no code or index
+    arithmetic with the time-domain loops of modwt_step (transforms_maximal_overlap.jl:9-29): level j is a circular
+    convolution with the filter up-sampled by 2^(j-1) (the a-trous cascade, Percival & Walden eq. 169), i.e. in the DFT
+    domain   V_j[k] = G[(2^(j-1) k) mod N] V_(j-1)[k],   W_j[k] = H[(2^(j-1) k) mod N] V_(j-1)[k]
+    with G, H the N-point DFTs of the reversed qmf / its mirror, both scaled by 1/sqrt(2) (modwt, :50-52)."""
+    q = np.asarray(wavelet(getattr(WT, wname)).qmf, dtype=np.float64)
+    g = q[::-1] / np.sqrt(2)                                        # scfilter = reverse(h)
+    h = q * (-1.0) ** np.arange(len(q)) / np.sqrt(2)                # dcfilter = mirror(h)
+    x = rng(n).standard_normal(n)
+    L = int(np.floor(np.log2(n)))
+    k = np.arange(n)
+    ph = np.exp(-2j * np.pi * np.outer(k, np.arange(len(q))) / n)   # ph[k, m] = e^{-2 pi i k m / N}
+    G, H = ph @ g, ph @ h
+    V = np.fft.fft(x)
+    cols = []
+    for j in range(1, L + 1):
+        idx = (k * (1 << (j - 1))) % n
+        cols.append(np.fft.ifft(H[idx] * V).real)
+        V = G[idx] * V
+    ref = np.stack(cols + [np.fft.ifft(V).real], axis=1)
+    W = orc.modwt(x, q, L)
+    assert W.shape == ref.shape
+    assert np.max(np.abs(W - ref)) <= 1e-12 * max(1.0, np.max(np.abs(x))) * L
+    # and the inverse against the same statement run backwards (conj: the synthesis filters are the time reverses)
+    Vb = np.fft.fft(ref[:, L])
+    for j in range(L, 0, -1):
+        idx = (k * (1 << (j - 1))) % n
+        Vb = np.conj(G[idx]) * Vb + np.conj(H[idx]) * np.fft.fft(ref[:, j - 1])
+    assert np.max(np.abs(orc.imodwt(W, q) - np.fft.ifft(Vb).real)) <= 1e-11
 
 
 def test_modwt_float32():

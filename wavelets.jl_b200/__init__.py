@@ -14,7 +14,7 @@ from . import util as Util
 from .wt import wavelet
 from .util import maxtransformlevels, maketree, isvalidtree, detailindex, detailrange, detailn
 from .transforms import (modwt, imodwt, maxmodwttransformlevels, dwt, idwt, dwt_, idwt_, wpt, iwpt, wpt_, iwpt_, dwtc, idwtc, dwt_oop_, idwt_oop_,
-                         ArgumentError, DimensionMismatch, set_strict_fp, colmajor)
+                         ArgumentError, DimensionMismatch, set_strict_fp, colmajor, release_scratch)
 from . import threshold as Threshold
 from .threshold import (HardTH, SoftTH, SemiSoftTH, SteinTH, BiggestTH, PosTH, NegTH, threshold, threshold_, VisuShrink, denoise, noisest,
                         ShannonEntropy, LogEnergyEntropy, coefentropy, bestbasistree)
@@ -22,5 +22,5 @@ from .threshold import (HardTH, SoftTH, SemiSoftTH, SteinTH, BiggestTH, PosTH, N
 __all__ = ["modwt", "imodwt", "maxmodwttransformlevels", "WT", "Util", "wavelet", "maxtransformlevels", "maketree", "isvalidtree", "detailindex",
            "detailrange", "detailn", "dwt", "idwt", "dwt_", "idwt_", "wpt", "iwpt", "wpt_", "iwpt_",
            "dwtc", "idwtc", "dwt_oop_", "idwt_oop_", "ArgumentError", "DimensionMismatch",
-           "set_strict_fp", "colmajor", "Threshold", "HardTH", "SoftTH", "SemiSoftTH", "SteinTH", "BiggestTH", "PosTH", "NegTH",
+           "set_strict_fp", "colmajor", "release_scratch", "Threshold", "HardTH", "SoftTH", "SemiSoftTH", "SteinTH", "BiggestTH", "PosTH", "NegTH",
            "threshold", "threshold_", "VisuShrink", "denoise", "noisest", "ShannonEntropy", "LogEnergyEntropy", "coefentropy", "bestbasistree"]

@@ -21,7 +21,8 @@ F32, F64, C64, C128 = range(4)
 FLAG_STRICT_FP = 1
 FLAG_FORCE_GENERIC = 2
 
-# every symbol include/wavelets_b200.h declares (tests/test_abi.py checks the .so exports all of them)
+# every symbol include/wavelets_b200.h declares (tests/test_host_logic.py::test_abi_exports_every_declared_symbol checks
+# the .so exports all of them)
 SYMBOLS = [
     "wb200_dwt_filter", "wb200_dwt_lifting", "wb200_wpt_filter", "wb200_wpt_lifting",
     "wb200_dwt_filter_host", "wb200_dwt_lifting_host", "wb200_workspace_bytes",
@@ -29,6 +30,7 @@ SYMBOLS = [
     "wb200_last_error_string", "wb200_version", "wb200_launch_count",
     "wb200_profile_enable", "wb200_profile_collect",
     "wb200_modwt", "wb200_imodwt", "wb200_maxmodwttransformlevels",
+    "wb200_trim_pool",
     "wb200_threshold", "wb200_threshold_biggest", "wb200_noisest", "wb200_denoise", "wb200_coefentropy", "wb200_bestbasistree",
 ]
 
@@ -68,7 +70,7 @@ def lib() -> C.CDLL:
     L.wb200_threshold.restype = i32
     L.wb200_threshold_biggest.argtypes = [vp, i64, i64, i32, vp]
     L.wb200_threshold_biggest.restype = i32
-    L.wb200_noisest.argtypes = [pd, vp, i32, C.POINTER(i64), i32, pd, i32, C.POINTER(LiftStep), i32, C.c_double, C.c_double, i32, vp, u32]
+    L.wb200_noisest.argtypes = [pd, vp, i32, C.POINTER(i64), i32, pd, i32, C.POINTER(LiftStep), i32, C.c_double, C.c_double, i32, i32, vp, u32]
     L.wb200_noisest.restype = i32
     L.wb200_denoise.argtypes = [vp, vp, i32, C.POINTER(i64), i32, pd, i32, C.POINTER(LiftStep), i32, C.c_double, C.c_double, i32,
                                 i32, C.c_double, C.c_double, i32, C.POINTER(i32), i32, vp, u32]
@@ -86,6 +88,8 @@ def lib() -> C.CDLL:
     L.wb200_last_error_string.restype = C.c_char_p
     L.wb200_launch_count.argtypes = [i32]
     L.wb200_launch_count.restype = i64
+    L.wb200_trim_pool.argtypes = [i64]
+    L.wb200_trim_pool.restype = i64
     L.wb200_profile_enable.argtypes = [i32]
     L.wb200_profile_enable.restype = None
     L.wb200_profile_collect.argtypes = [C.c_char_p, i64]

@@ -88,22 +88,45 @@ static bool isvalidtree(int64_t n, const uint8_t *b, int64_t nb) {
 // ---------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t b) { return (b + 255) & ~(size_t)255; }
 
-// The stream-ordered pool returns freed memory to the OS at the next synchronisation unless told otherwise; a transform
-// called in a loop would then re-map its scratch (milliseconds per GB) on every call.  Raise the release threshold of the
-// device's default pool once per device: scratch stays reserved for reuse (cudaMemPoolTrimTo releases it on request).
-void keep_pool_memory() {
-    static std::mutex mu;
-    static bool done[64] = {false};
+// Scratch comes from a LIBRARY-PRIVATE stream-ordered pool (one per device, created on first use), not from the device's
+// default pool: the default pool hands freed memory back to the OS at the next synchronisation, so a transform called
+// in a loop would re-map its scratch (milliseconds per GB) on every call; keeping it needs a raised release threshold,
+// and raising it on the DEFAULT pool would change the behaviour of every other cudaMallocAsync user in the process.
+// The private pool keeps what it has been given until wb200_trim_pool() (or process exit) releases it.
+static std::mutex g_pool_mu;
+static cudaMemPool_t g_pools[64] = {nullptr};
+static cudaMemPool_t scratch_pool() {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { (void)cudaGetLastError(); return; }
-    std::lock_guard<std::mutex> lk(mu);
-    if (done[dev]) return;
-    done[dev] = true;
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        uint64_t thr = ~0ull;
-        if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr) != cudaSuccess) (void)cudaGetLastError();
-    } else (void)cudaGetLastError();
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { (void)cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pools[dev]) return g_pools[dev];
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    uint64_t thr = ~0ull;
+    if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr) != cudaSuccess) (void)cudaGetLastError();
+    g_pools[dev] = pool;
+    return pool;
+}
+cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t st) {
+    cudaMemPool_t pool = scratch_pool();
+    if (pool) return cudaMallocFromPoolAsync(p, bytes, pool, st);
+    return cudaMallocAsync(p, bytes, st);          // pool creation refused: the default pool (its own threshold) still works
+}
+int64_t trim_pool(int64_t keep_bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { (void)cudaGetLastError(); return -1; }
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (!g_pools[dev]) return 0;
+    if (cudaMemPoolTrimTo(g_pools[dev], keep_bytes > 0 ? (size_t)keep_bytes : 0) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+    uint64_t reserved = 0;
+    if (cudaMemPoolGetAttribute(g_pools[dev], cudaMemPoolAttrReservedMemCurrent, &reserved) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+    return (int64_t)reserved;
 }
 
 struct Workspace {
@@ -122,8 +145,7 @@ struct Workspace {
             base = (char *)user; size = user_bytes;
             return WB200_OK;
         }
-        keep_pool_memory();
-        if (!cuda_ok(cudaMallocAsync((void **)&base, need, stream), "cudaMallocAsync(workspace)")) return WB200_ECUDA;
+        if (!cuda_ok(scratch_alloc((void **)&base, need, stream), "cudaMallocAsync(workspace)")) return WB200_ECUDA;
         size = need; owned = true;
         return WB200_OK;
     }
@@ -582,6 +604,7 @@ extern "C" int64_t wb200_launch_count(int32_t reset) {
     if (reset) g_launches = 0;
     return v;
 }
+extern "C" int64_t wb200_trim_pool(int64_t keep_bytes) { return trim_pool(keep_bytes); }
 extern "C" void wb200_profile_enable(int32_t on) { g_prof_on = on != 0; }
 // Waits for the recorded launches, then writes one line per kernel name: "<name> <launches> <total_ms>\n".
 // Returns the number of bytes written (0 when nothing was recorded).  Clears the record.

@@ -74,8 +74,7 @@ int32_t entropies(std::vector<double> &bf, std::vector<double> &af, const T *y, 
     const size_t arr = (((size_t)n * sizeof(T)) + 255) & ~(size_t)255;
     const size_t ent_bytes = (size_t)(ntree + n_af) * sizeof(double);
     char *pool = nullptr;
-    keep_pool_memory();
-    if (cudaMallocAsync((void **)&pool, 2 * arr + ent_bytes + NPART * sizeof(double) + 256, st) != cudaSuccess) {
+    if (scratch_alloc((void **)&pool, 2 * arr + ent_bytes + NPART * sizeof(double) + 256, st) != cudaSuccess) {
         (void)cudaGetLastError(); set_error("cudaMallocAsync(bestbasis scratch) failed"); return WB200_ECUDA;
     }
     T *xa = (T *)pool, *xb = (T *)(pool + arr);
@@ -132,8 +131,7 @@ extern "C" int32_t wb200_coefentropy(double *out, const void *x, int64_t count, 
     if (count == 0) return WB200_OK;
     cudaStream_t st = (cudaStream_t)stream;
     char *pool = nullptr;
-    keep_pool_memory();
-    if (cudaMallocAsync((void **)&pool, (NPART + 2) * sizeof(double) + 64, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync failed"); return WB200_ECUDA; }
+    if (scratch_alloc((void **)&pool, (NPART + 2) * sizeof(double) + 64, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync failed"); return WB200_ECUDA; }
     double *part = (double *)pool, *res = part + NPART;
     void *nrmp = (void *)(res + 1);
     {
@@ -173,9 +171,19 @@ extern "C" int32_t wb200_bestbasistree(uint8_t *besttree, double *entr_bf, doubl
     if (dtype == WB200_F64) rc = entropies<double>(bf, af, (const double *)y, n, Lmax, wkind, qmf, flen, steps, nsteps, norm1, norm2, et, dtype, st, flags);
     else                    rc = entropies<float>(bf, af, (const float *)y, n, Lmax, wkind, qmf, flen, steps, nsteps, norm1, norm2, et, dtype, st, flags);
     if (rc != WB200_OK) return rc;
+    const double tie_rel = (dtype == WB200_F64) ? 1e-13 : 1e-6;
     for (int64_t i = 1; i <= ntree; ++i) {                  // entropy.jl:93-105
         if ((i > 1 && !besttree[(i >> 1) - 1]) || !tree[i - 1]) besttree[i - 1] = 0;
-        else besttree[i - 1] = (bf[(size_t)(i - 1)] <= bestsub(bf, af, i)) ? 0 : 1;
+        else {
+            // Upstream decides `entr_bf[i] <= bestsubtree_entropy(...)` on sums accumulated sequentially in T; here the sums
+            // are block-reduced in double, so two entropies that are EQUAL upstream (exact ties: a node and its children
+            // carrying the same cost, e.g. all-zero nodes or Haar on piecewise-constant data) may differ here in the last
+            // bits.  Ties are resolved the way upstream's `<=` resolves them -- the node is NOT split -- by comparing with
+            // a relative slack of a few rounding errors of T-precision sums.
+            const double a = bf[(size_t)(i - 1)], b = bestsub(bf, af, i);
+            const double slack = tie_rel * std::fmax(std::fabs(a), std::fabs(b));
+            besttree[i - 1] = (a <= b + slack) ? 0 : 1;
+        }
     }
     if (entr_bf) for (int64_t i = 0; i < ntree; ++i) entr_bf[i] = bf[(size_t)i];
     if (entr_af) for (size_t i = 0; i < af.size(); ++i) entr_af[i] = af[i];

@@ -74,7 +74,7 @@ template <typename T> struct LiftScheme {
 // error plumbing (thread-local detail string + launch counter), defined in api.cu
 // ---------------------------------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
-void keep_pool_memory();              // raise the default stream-ordered pool's release threshold (once per device), api.cu
+cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t st);   // library-private stream-ordered pool (api.cu); free with cudaFreeAsync
 bool check_launch(const char *what); // cudaGetLastError after a launch; records the error
 // Every kernel launch sits inside a LaunchScope: it bumps the per-thread launch counter and, when profiling is
 // enabled (wb200_profile_enable), brackets the launch with CUDA events on the launching stream so bench.py can

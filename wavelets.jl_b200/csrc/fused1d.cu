@@ -524,8 +524,7 @@ static int32_t run_fused_1d(const PassOp<T> &op, T *y, const T *x, int64_t n, in
             if (ws_bytes < scratch_bytes) { set_error("workspace too small: %zu bytes given, %zu needed", ws_bytes, scratch_bytes); return WB200_EWORKSPACE; }
             scratch = (T *)workspace;
         } else {
-            keep_pool_memory();
-            if (cudaMallocAsync((void **)&scratch, scratch_bytes, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(fused scratch) failed"); return WB200_ECUDA; }
+            if (scratch_alloc((void **)&scratch, scratch_bytes, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(fused scratch) failed"); return WB200_ECUDA; }
             own_scratch = true;
         }
     }

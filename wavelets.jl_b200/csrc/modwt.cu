@@ -763,8 +763,7 @@ static int32_t modwt_common(void *out, const void *in, int64_t n, int64_t batch,
     void *scratch = workspace;
     bool own = false;
     if (workspace == nullptr) {
-        keep_pool_memory();
-        if (cudaMallocAsync(&scratch, need, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(modwt scratch) failed"); return WB200_ECUDA; }
+        if (scratch_alloc(&scratch, need, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(modwt scratch) failed"); return WB200_ECUDA; }
         own = true;
     } else if (ws_bytes < need) { set_error("workspace too small: %zu bytes given, %zu needed", ws_bytes, need); return WB200_EWORKSPACE; }
     ModwtTaps tp;

@@ -260,17 +260,21 @@ bool check_wt(const WtArgs &w) {
 // noisest on the device: *sigma_dev = mad(y[n1/2 : n1]) / 0.6745, y = level-1 transform of x (or x itself).  tmp: tot elements.
 template <typename T>
 int32_t noisest_dev(double *sigma_dev, const T *x, int32_t ndim, const int64_t *dims, int64_t tot, const WtArgs &w, T *tmp,
-                    SelBuf *sb, T *med, int32_t dtype, cudaStream_t st, uint32_t flags) {
-    const int64_t n1 = dims[0], lo = (int64_t)std::nearbyint((double)n1 / 2 + 1) - 1, m = n1 - lo;   // round(Int, .): ties to even
-    if (m < 1) { set_error("noisest: no detail coefficients (size(x,1) = %lld)", (long long)n1); return WB200_EDIMS; }
+                    SelBuf *sb, T *med, int32_t dtype, cudaStream_t st, uint32_t flags, int32_t L = 1) {
+    // detailrange(size(y, 1), L) = round(n1/2^L + 1) : round(n1/2^(L-1)) (src/Util/non_dyadic.jl:9), as LINEAR indices into y;
+    // round(Int, .): ties to even
+    if (L < 1 || L > 60) { set_error("L must be positive"); return WB200_ELEVEL; }
+    const int64_t n1 = dims[0], lo = (int64_t)std::nearbyint((double)n1 / (double)((int64_t)1 << L) + 1) - 1,
+                  hi = (int64_t)std::nearbyint((double)n1 / (double)((int64_t)1 << (L - 1))), m = hi - lo;
+    if (m < 1 || hi > tot) { set_error("noisest: no detail coefficients at level %d (size(x,1) = %lld)", (int)L, (long long)n1); return WB200_EDIMS; }
     if (w.wkind == 0) {
         if (cudaMemcpyAsync(tmp, x + lo, sizeof(T) * (size_t)m, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { (void)cudaGetLastError(); return WB200_ECUDA; }
     } else {
-        const int32_t rc = xform(tmp, x, ndim, dims, w, 1, 1, dtype, (void *)st, flags);
+        const int32_t rc = xform(tmp, x, ndim, dims, w, L, 1, dtype, (void *)st, flags);
         if (rc != WB200_OK) return rc;
         if (lo > 0 && cudaMemcpyAsync(tmp, tmp + lo, sizeof(T) * (size_t)m, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { (void)cudaGetLastError(); return WB200_ECUDA; }
     }
-    // (the copy ranges [lo, lo+m) and [0, m) may overlap only if lo < m, i.e. never: lo = n1/2 = m)
+    // (the copy ranges [lo, lo+m) and [0, m) never overlap: m = hi - lo <= lo for every L >= 1)
     return device_mad<T>(tmp, m, sb, med, sigma_dev, st) ? WB200_OK : WB200_ECUDA;
 }
 
@@ -298,8 +302,7 @@ int32_t denoise_t(T *y, const T *x, int32_t ndim, const int64_t *dims, const WtA
     const size_t arr = (((size_t)tot * (size_t)chunk * sizeof(T)) + 255) & ~(size_t)255;
     const int narr = TI ? 2 : 1;
     char *pool = nullptr;
-    keep_pool_memory();
-    if (cudaMallocAsync((void **)&pool, narr * arr + 4096, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(denoise scratch) failed"); return WB200_ECUDA; }
+    if (scratch_alloc((void **)&pool, narr * arr + 4096, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(denoise scratch) failed"); return WB200_ECUDA; }
     T *a0 = (T *)pool, *a1 = (T *)(pool + (narr > 1 ? arr : 0));
     SelBuf *sb = (SelBuf *)(pool + narr * arr);
     T *med = (T *)(pool + narr * arr + 3072);
@@ -369,8 +372,7 @@ extern "C" int32_t wb200_threshold_biggest(void *x, int64_t count, int64_t m, in
     const size_t esz = dtype == WB200_F64 ? 8 : 4;
     if (m == 0) return cudaMemsetAsync(x, 0, (size_t)count * esz, st) == cudaSuccess ? WB200_OK : WB200_ECUDA;
     SelBuf *sb = nullptr;
-    keep_pool_memory();
-    if (cudaMallocAsync((void **)&sb, sizeof(SelBuf), st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(select state) failed"); return WB200_ECUDA; }
+    if (scratch_alloc((void **)&sb, sizeof(SelBuf), st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(select state) failed"); return WB200_ECUDA; }
     const unsigned g = grid_for_n(count);
     const long long k = (long long)(count - m);
     { LaunchScope scope("select_init", st); k_sel_init<<<1, 256, 0, st>>>(sb, k, k); }
@@ -394,7 +396,7 @@ extern "C" int32_t wb200_threshold_biggest(void *x, int64_t count, int64_t m, in
 
 extern "C" int32_t wb200_noisest(double *sigma_out, const void *x, int32_t ndim, const int64_t *dims, int32_t wkind,
                                  const double *qmf, int32_t flen, const wb200_lift_step *steps, int32_t nsteps, double norm1,
-                                 double norm2, int32_t dtype, void *stream, uint32_t flags) {
+                                 double norm2, int32_t L, int32_t dtype, void *stream, uint32_t flags) {
     if (dtype != WB200_F32 && dtype != WB200_F64) { set_error("noisest supports Float32/Float64"); return WB200_EDTYPE; }
     if (sigma_out == nullptr || x == nullptr || dims == nullptr || ndim < 1 || ndim > 3) { set_error("bad argument"); return WB200_EARG; }
     const WtArgs w{wkind, qmf, flen, steps, nsteps, norm1, norm2};
@@ -405,13 +407,12 @@ extern "C" int32_t wb200_noisest(double *sigma_out, const void *x, int32_t ndim,
     const size_t esz = dtype == WB200_F64 ? 8 : 4;
     const size_t arr = (((size_t)tot * esz) + 255) & ~(size_t)255;
     char *pool = nullptr;
-    keep_pool_memory();
-    if (cudaMallocAsync((void **)&pool, arr + 4096, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(noisest scratch) failed"); return WB200_ECUDA; }
+    if (scratch_alloc((void **)&pool, arr + 4096, st) != cudaSuccess) { (void)cudaGetLastError(); set_error("cudaMallocAsync(noisest scratch) failed"); return WB200_ECUDA; }
     SelBuf *sb = (SelBuf *)(pool + arr);
     double *sig = (double *)(pool + arr + 3072 + 64);
     int32_t rc;
-    if (dtype == WB200_F64) rc = noisest_dev<double>(sig, (const double *)x, ndim, dims, tot, w, (double *)pool, sb, (double *)(pool + arr + 3072), dtype, st, flags);
-    else                    rc = noisest_dev<float>(sig, (const float *)x, ndim, dims, tot, w, (float *)pool, sb, (float *)(pool + arr + 3072), dtype, st, flags);
+    if (dtype == WB200_F64) rc = noisest_dev<double>(sig, (const double *)x, ndim, dims, tot, w, (double *)pool, sb, (double *)(pool + arr + 3072), dtype, st, flags, L);
+    else                    rc = noisest_dev<float>(sig, (const float *)x, ndim, dims, tot, w, (float *)pool, sb, (float *)(pool + arr + 3072), dtype, st, flags, L);
     if (rc == WB200_OK) {
         if (cudaMemcpyAsync(sigma_out, sig, sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
             (void)cudaGetLastError(); set_error("noisest: copy of the result failed"); rc = WB200_ECUDA;

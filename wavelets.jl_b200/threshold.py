@@ -126,16 +126,14 @@ def _wt_args(wt):
 
 
 def noisest(x, wt=DEFAULT_WAVELET, L: int = 1) -> float:
-    """noisest(x, wt): MAD of the level-1 detail coefficients y[detailrange(y, 1)] over 0.6745 (denoising.jl:88-98).
+    """noisest(x, wt, L=1): MAD of y[detailrange(y, L)], y = dwt(x, wt, L), over 0.6745 (denoising.jl:94-101).
     Returns a Python float (the one call of this module that waits for the stream)."""
-    if L != 1:
-        raise NotImplementedError("noisest: only L = 1 (the reference's default) is on the device path")
     x = _real(x)
     wk, qp, fl, st, ns, n1, n2, keep = _wt_args(wt)
     out = C.c_double(0.0)
     dims = _lib.dims_array(list(x.shape))
     with torch.cuda.device(x.device):
-        rc = _lib.lib().wb200_noisest(C.byref(out), x.data_ptr(), x.dim(), dims, wk, qp, fl, st, ns, n1, n2, _DTYPES[x.dtype],
+        rc = _lib.lib().wb200_noisest(C.byref(out), x.data_ptr(), x.dim(), dims, wk, qp, fl, st, ns, n1, n2, int(L), _DTYPES[x.dtype],
                                       _stream(x), _flags_value())
     _check(rc)
     return out.value

@@ -22,7 +22,7 @@ from .util import iscube, isvalidtree, maketree, maxtransformlevels, sufficientp
 from .wt import GLS, OrthoFilter
 
 __all__ = ["modwt", "imodwt", "maxmodwttransformlevels", "dwt", "idwt", "dwt_", "idwt_", "wpt", "iwpt", "wpt_", "iwpt_", "dwtc", "idwtc",
-           "dwt_oop_", "idwt_oop_", "ArgumentError", "DimensionMismatch", "set_strict_fp", "colmajor"]
+           "dwt_oop_", "idwt_oop_", "ArgumentError", "DimensionMismatch", "set_strict_fp", "colmajor", "release_scratch"]
 
 
 class ArgumentError(ValueError):
@@ -46,6 +46,18 @@ def set_strict_fp(on: bool) -> None:
     """strict = no FMA contraction: results bit-identical to the reference CPU path (slower)."""
     global _flags
     _flags = (_flags | _lib.FLAG_STRICT_FP) if on else (_flags & ~_lib.FLAG_STRICT_FP)
+
+
+def release_scratch(keep_bytes: int = 0, device=None) -> int:
+    """Give the library's cached device scratch (its private stream-ordered pool) back to the device, keeping at most
+    `keep_bytes`; returns the bytes still reserved.  Calls made without a caller workspace re-reserve on demand."""
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    with torch.cuda.device(dev):
+        torch.cuda.synchronize()
+        left = int(_lib.lib().wb200_trim_pool(int(keep_bytes)))
+    if left < 0:
+        raise RuntimeError("wb200_trim_pool failed")
+    return left
 
 
 def _flags_value() -> int:
@@ -110,6 +122,26 @@ def _prep(x) -> torch.Tensor:
     return colmajor(x)
 
 
+def _check_out(y, x: torch.Tensor, what: str) -> None:
+    """The destination of an out-of-place call: a column-major CUDA tensor on x's device with x's element type and shape
+    (the kernels write dense column-major elements of x's width through y's pointer)."""
+    if not isinstance(y, torch.Tensor) or not y.is_cuda:
+        raise TypeError(f"{what}: y must be a torch CUDA tensor")
+    if y.device != x.device:
+        raise TypeError(f"{what}: y and x must live on the same device")
+    if y.dtype not in _DTYPES or y.dtype != x.dtype:
+        raise TypeError(f"{what}: y must have x's element type ({x.dtype}), got {y.dtype}")
+    if tuple(x.shape) != tuple(y.shape):
+        raise DimensionMismatch("in and out array size must match")
+    if not _is_colmajor(y):
+        raise TypeError(f"{what}: y must be column-major (Julia layout); see colmajor()")
+
+
+def _check_inplace(y, what: str) -> None:
+    if not isinstance(y, torch.Tensor) or not y.is_cuda or y.dtype not in _DTYPES or not _is_colmajor(y):
+        raise TypeError(f"{what}: y must be a column-major floating CUDA tensor (transformed in place)")
+
+
 def _stream(x: torch.Tensor):
     return C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
 
@@ -167,8 +199,7 @@ def _xwt_bang(args, fw: bool):
     if len(args) >= 2 and isinstance(args[1], GLS):
         y, scheme = args[0], args[1]
         L = args[2] if len(args) > 2 else None
-        if not isinstance(y, torch.Tensor) or not y.is_cuda or y.dtype not in _DTYPES or not _is_colmajor(y):
-            raise TypeError("dwt_(y, scheme): y must be a column-major floating CUDA tensor (transformed in place)")
+        _check_inplace(y, "dwt_(y, scheme)")
         if L is None:
             L = maxtransformlevels(y)
         _call_dwt(y, y, scheme, L, fw, y.dim(), 1)
@@ -176,11 +207,8 @@ def _xwt_bang(args, fw: bool):
     if len(args) >= 3 and isinstance(args[2], OrthoFilter):
         y, x, filt = args[0], args[1], args[2]
         L = args[3] if len(args) > 3 else None
-        if not isinstance(y, torch.Tensor) or not y.is_cuda or not _is_colmajor(y):
-            raise TypeError("dwt_(y, x, filter): y must be a column-major CUDA tensor")
         x = _prep(x)
-        if tuple(x.shape) != tuple(y.shape) or x.dtype != y.dtype:
-            raise DimensionMismatch("in and out array size must match")
+        _check_out(y, x, "dwt_(y, x, filter)")
         if L is None:
             L = maxtransformlevels(x)
         if y.data_ptr() == x.data_ptr():
@@ -204,8 +232,7 @@ def dwt_oop_(y, x, wt, L=None):
     """dwt_oop!(y, x, wt, L) -- transforms_main.jl:193-207: out of place for both transform types."""
     if isinstance(wt, GLS):
         x = _prep(x)
-        if tuple(x.shape) != tuple(y.shape):
-            raise DimensionMismatch("in and out array size must match")
+        _check_out(y, x, "dwt_oop_(y, x, scheme)")
         if L is None:
             L = maxtransformlevels(x)
         _call_dwt(y, x, wt, L, True, x.dim(), 1)
@@ -216,8 +243,7 @@ def dwt_oop_(y, x, wt, L=None):
 def idwt_oop_(y, x, wt, L=None):
     if isinstance(wt, GLS):
         x = _prep(x)
-        if tuple(x.shape) != tuple(y.shape):
-            raise DimensionMismatch("in and out array size must match")
+        _check_out(y, x, "idwt_oop_(y, x, scheme)")
         if L is None:
             L = maxtransformlevels(x)
         _call_dwt(y, x, wt, L, False, x.dim(), 1)
@@ -303,13 +329,17 @@ def _xwpt_bang(args, fw: bool):
     # wpt!(y, x, filter[, L | tree]) | wpt!(y, scheme[, L | tree])        transforms_main.jl:147-158, 166-175
     if len(args) >= 2 and isinstance(args[1], GLS):
         y, scheme = args[0], args[1]
+        _check_inplace(y, "wpt_(y, scheme)")
+        if y.dim() not in (1, 2):
+            raise DimensionMismatch("wpt expects a vector (or an (n, B) batch of columns)")
         tree = _tree_arg(y, args[2] if len(args) > 2 else None)
         _call_wpt(y, y, scheme, tree, fw, 1 if y.dim() == 1 else int(y.shape[1]))
         return y
     if len(args) >= 3 and isinstance(args[2], OrthoFilter):
         y, x, filt = args[0], _prep(args[1]), args[2]
-        if tuple(x.shape) != tuple(y.shape):
-            raise DimensionMismatch("in and out array size must match")
+        _check_out(y, x, "wpt_(y, x, filter)")
+        if x.dim() not in (1, 2):
+            raise DimensionMismatch("wpt expects a vector (or an (n, B) batch of columns)")
         if y.data_ptr() == x.data_ptr():
             raise ArgumentError("in array is out array")
         tree = _tree_arg(x, args[3] if len(args) > 3 else None)

@@ -86,7 +86,7 @@ def isvalidtree(x, b) -> bool:
     b = np.asarray(b)
     if len(b) != 2 ** ns - 1:
         return False
-    for i in range(1, 2 ** (ns - 1)):
+    for i in range(1, 1 << max(ns - 1, 0)):
         if not b[i - 1] and (b[2 * i - 1] or b[2 * i]):
             return False
     return True
