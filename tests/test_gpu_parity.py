@@ -695,13 +695,52 @@ def test_fused_fir3d_vs_oracle(dev, mode, dtype, wname):
         xr = wb.idwt(y, wt, L)
         _lib.lib().wb200_profile_enable(0)
         names = _kernel_names()
-        assert {"fused_fir2d_fwd", "fused_fir2d_inv"} <= names, names
+        assert ({"fused_fir2d_fwd", "fused_fir2d_inv"} <= names) or ({"fused_fir3d_fwd", "fused_fir3d_inv"} <= names), names
         check(y, orc.dwt_filter(x, wt.qmf, L), mode, 3 * L, 8.0)
         check(xr, orc.dwt_filter(to_np(y), wt.qmf, L, fw=False), mode, 3 * L, 8.0)
     xb = rng(3).standard_normal((128, 128, 4, 2)).astype(dtype)          # two volumes
     yb = wb.dwtc(to_gpu(xb, dev), wt, 2)
     check(yb, orc.dwt_filter_batch(xb, 3, wt.qmf, 2), mode, 6, 8.0)
     check(wb.idwtc(yb, wt, 2), orc.dwt_filter_batch(to_np(yb), 3, wt.qmf, 2, fw=False), mode, 6, 8.0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("wname", ["haar", "db2", "db4", "db6", "sym8", "db10"])
+def test_onepass_fir3d_vs_oracle(dev, mode, dtype, wname):
+    """One-pass marching 3-D level kernels (fir3d_impl.cuh): one launch per level reads the corner once and writes its
+    eight octants.  Cube with a generic remainder (and the parked-corner inverse of a single fused level), a non-cube
+    volume with two fused levels, and a batch."""
+    from wavelets_b200 import _lib
+    wt = wavelet(wavelet_class(wname))
+    for shape, L in (((128, 128, 128), 3), ((256, 128, 64), 2), ((128, 64, 32), 1)):
+        x = rng(sum(shape) + L + len(wname)).standard_normal(shape).astype(dtype)
+        _lib.lib().wb200_profile_enable(1)
+        y = wb.dwt(to_gpu(x, dev), wt, L)
+        xr = wb.idwt(y, wt, L)
+        _lib.lib().wb200_profile_enable(0)
+        names = _kernel_names()
+        assert {"fused_fir3d_fwd", "fused_fir3d_inv"} <= names, names
+        check(y, orc.dwt_filter(x, wt.qmf, L), mode, 3 * L, 8.0)
+        check(xr, orc.dwt_filter(to_np(y), wt.qmf, L, fw=False), mode, 3 * L, 8.0)
+    xb = rng(7).standard_normal((128, 32, 32, 3)).astype(dtype)          # three volumes in one launch
+    yb = wb.dwtc(to_gpu(xb, dev), wt, 2)
+    check(yb, orc.dwt_filter_batch(xb, 3, wt.qmf, 2), mode, 6, 8.0)
+    check(wb.idwtc(yb, wt, 2), orc.dwt_filter_batch(to_np(yb), 3, wt.qmf, 2, fw=False), mode, 6, 8.0)
+
+
+@pytest.mark.parametrize("chunks", ["1", "2", "16"])
+def test_onepass_fir3d_chunks_of_the_marching_dimension(dev, monkeypatch, chunks):
+    """Every split of the marching dimension (warm-up slabs re-read across the periodic seam) gives the same bits."""
+    monkeypatch.setenv("WB200_FIR3D_CHUNKS", chunks)
+    wt = wavelet(WT.db6)
+    x = rng(33).standard_normal((128, 64, 64)).astype(np.float32)
+    wb.set_strict_fp(True)
+    try:
+        y = wb.dwt(to_gpu(x, dev), wt, 1)
+        assert np.array_equal(to_np(y), orc.dwt_filter(x, wt.qmf, 1))
+        assert np.array_equal(to_np(wb.idwt(y, wt, 1)), orc.dwt_filter(to_np(y), wt.qmf, 1, fw=False))
+    finally:
+        wb.set_strict_fp(False)
 
 
 # ------------------------------------------------------------------------------------------------------

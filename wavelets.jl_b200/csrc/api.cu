@@ -576,6 +576,41 @@ static int32_t dispatch_dwt(PassOp<T> &op, void *y, const void *x, const Call &c
             return fused2d_run<T>(op, (T *)y, xin, (const T *)scratch, nr, nr * nr, g, Lf, false, scratch, st);
         }
     }
+    // 3-D orthogonal filter bank: one-pass marching level kernels (fir3d_impl.cuh) for the levels whose corner is whole
+    // tiles, the generic / line passes for the small remainder
+    if (!(flags & WB200_FLAG_FORCE_GENERIC) && g.C == 1 && g.ndim == 3 && !lifting &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+        const int Lf = fir3d_levels<T>(op, g, L, fw);
+        if (Lf > 0) {
+            const int64_t N1 = g.dim[0], N2 = g.dim[1], N3 = g.dim[2];
+            const int64_t r1 = N1 >> Lf, r2 = N2 >> Lf, r3 = N3 >> Lf;          // corner left to the remainder
+            const bool park = !fw && L > Lf && Lf == 1;                        // the single fused level would read y's corner while y is written
+            const size_t park_bytes = park ? align_up((size_t)(r1 * r2 * r3 * g.batch) * sizeof(T)) : 0;
+            const size_t need = align_up(fir3d_scratch_bytes<T>(g, Lf)) + 512 + park_bytes + (L > Lf ? plan_nd_from(c, Lf + 1) : 0);
+            Workspace ws;
+            int32_t rc = ws.init(workspace, ws_bytes, need, st);
+            if (rc != WB200_OK) return rc;
+            T *scratch = (T *)ws.take(fir3d_scratch_bytes<T>(g, Lf) + 256);
+            T *parked = park ? (T *)ws.take(park_bytes) : nullptr;
+            if (!scratch || (park && !parked)) { set_error("internal: fused 3-D workspace plan mismatch"); return WB200_EWORKSPACE; }
+            const T *xin = (const T *)x;
+            if (fw) {
+                rc = fir3d_run<T>(op, (T *)y, xin, nullptr, 0, 0, 0, g, Lf, true, scratch, st);
+                if (rc != WB200_OK || L == Lf) return rc;
+                return run_nd<T>(op, (T *)y, (const T *)y, g, L, true, ws, Lf + 1, L);
+            }
+            if (L == Lf) return fir3d_run<T>(op, (T *)y, xin, xin, N1, N1 * N2, g.slice(), g, Lf, false, scratch, st);
+            rc = run_nd<T>(op, (T *)y, xin, g, L, false, ws, Lf + 1, L);        // leaves the level-Lf approximation in y's corner
+            if (rc != WB200_OK) return rc;
+            if (!park) return fir3d_run<T>(op, (T *)y, xin, (const T *)y, N1, N1 * N2, g.slice(), g, Lf, false, scratch, st);
+            View<const T> vs; View<T> vd; Extent e;
+            e.len = r1; e.n[0] = 1; e.n[1] = r2; e.n[2] = r3; e.n[3] = g.batch;
+            vs.p = (const T *)y; vs.ls = 1; vs.s[0] = 0; vs.s[1] = N1; vs.s[2] = N1 * N2; vs.s[3] = g.slice();
+            vd.p = parked; vd.ls = 1; vd.s[0] = 0; vd.s[1] = r1; vd.s[2] = r1 * r2; vd.s[3] = r1 * r2 * r3;
+            if (!launch_copy_lines<T>(vs, vd, e, st)) return WB200_ECUDA;
+            return fir3d_run<T>(op, (T *)y, xin, parked, r1, r1 * r2, r1 * r2 * r3, g, Lf, false, scratch, st);
+        }
+    }
     Workspace ws;
     int32_t rc = ws.init(workspace, ws_bytes, plan_dwt(c, L, lifting, inplace, flags | WB200_FLAG_FORCE_GENERIC), st);
     if (rc != WB200_OK) return rc;

@@ -49,4 +49,14 @@ template <typename T>
 int32_t fir2d_level(const PassOp<T> &op, bool fw, const T *a, int64_t lda, int64_t bsa, const T *xd, int64_t ldx, int64_t bsx,
                     T *o1, int64_t ld1, int64_t bs1, T *o2, int64_t ld2, int64_t bs2, int n, int64_t B, cudaStream_t st);
 
+// ---- one-pass 3-D filter-bank levels (fir3d_f32.cu / fir3d_f64.cu, fir3d_impl.cuh) ----
+// Number of leading levels the marching kernels take (every dimension of the level's corner whole tiles), their LLL ping-pong
+// scratch, and the level walk (same contract as fused2d_run: forward leaves the level-Lf approximation in y's corner; inverse
+// reads it from ll_src with the given row / plane / batch strides -- never y itself when Lf == 1).
+template <typename T> int fir3d_levels(const PassOp<T> &op, const ArrayGeom &g, int L, bool fw);
+template <typename T> size_t fir3d_scratch_bytes(const ArrayGeom &g, int Lf);
+template <typename T>
+int32_t fir3d_run(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int64_t ll_ld, int64_t ll_ps, int64_t ll_bs,
+                  const ArrayGeom &g, int Lf, bool fw, void *scratch, cudaStream_t st);
+
 } // namespace wb
