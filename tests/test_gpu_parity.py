@@ -705,6 +705,56 @@ def test_fused_fir3d_vs_oracle(dev, mode, dtype, wname):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("wname", ["cdf97", "haar", "db2"])
+@pytest.mark.parametrize("tile,kmax", [(None, None), ("256", "3"), ("512", "2"), ("1024", "8")])
+def test_fused_lift1d_vs_oracle(dev, mode, dtype, wname, tile, kmax, monkeypatch):
+    """Fused multi-level 1-D lifting tile kernels (lift1d.cu): TMA-staged tiles with the cumulative halo of K levels,
+    register-resident predict / update steps, generic remainder.  Default plan and forced small tiles / level splits."""
+    from wavelets_b200 import _lib
+    if tile:
+        for v in ("WB200_LIFT1D_TILE_F32", "WB200_LIFT1D_TILE_F64"):
+            monkeypatch.setenv(v, tile)
+        monkeypatch.setenv("WB200_LIFT1D_KMAX", kmax)
+    wl = wavelet(getattr(WT, wname), WT.Lifting)
+    for n, B, L in ((1 << 16, 3, None), (3 * 4096, 2, 4), (8192, 1, 13), (4096, 5, 2)):
+        Lr = L if L is not None else wb.maxtransformlevels(n)
+        x = rng(n % 1000 + B).standard_normal((n, B)).astype(dtype)
+        _lib.lib().wb200_profile_enable(1)
+        y = wb.dwtc(to_gpu(x, dev), wl, Lr)
+        xr = wb.idwtc(y, wl, Lr)
+        _lib.lib().wb200_profile_enable(0)
+        names = _kernel_names()
+        assert {"fused_lift1d_ana", "fused_lift1d_syn"} <= names, names
+        ref = orc.dwt_lifting_batch(x, 1, wl.step, wl.norm1, wl.norm2, Lr)
+        check(y, ref, mode, Lr, 8.0)
+        check(xr, orc.dwt_lifting_batch(to_np(y), 1, wl.step, wl.norm1, wl.norm2, Lr, fw=False), mode, Lr, 8.0)
+    # the reference's own form: in place on a vector (dwt!(y, scheme, L)); same bits as the allocating form
+    x1 = rng(5).standard_normal(1 << 15).astype(dtype)
+    yi = to_gpu(x1, dev).clone()
+    wb.dwt_(yi, wl, 9)
+    assert torch.equal(yi, wb.dwt(to_gpu(x1, dev), wl, 9))
+    check(yi, orc.dwt_lifting(x1, wl.step, wl.norm1, wl.norm2, 9), mode, 9, 8.0)
+    wb.idwt_(yi, wl, 9)
+    check(yi, orc.dwt_lifting(orc.dwt_lifting(x1, wl.step, wl.norm1, wl.norm2, 9), wl.step, wl.norm1, wl.norm2, 9, fw=False), mode, 9, 8.0)
+
+
+def test_lift1d_full_size_strict_vs_oracle(dev):
+    """north_star's lifting leg at the 1-D BASELINE size: cdf97 lifting, N = 2^20, L = 20, a batch of columns; two columns
+    bit-identical to the oracle in strict mode, both directions, and the documented Float32 bar in fast mode."""
+    n, B = 1 << 20, 12
+    wl = wavelet(WT.cdf97, WT.Lifting)
+    x = rng(2021).standard_normal((n, B)).astype(np.float32)
+    xg = to_gpu(x, dev)
+    cols = [0, B - 1]
+    ref = np.stack([orc.dwt_lifting(x[:, b].copy(), wl.step, wl.norm1, wl.norm2, 20) for b in cols], axis=1)
+    _strict_then_fast(lambda: wb.dwtc(xg, wl)[:, cols], ref, 1e-5)
+    yg = wb.dwtc(xg, wl)
+    yg[:, cols] = torch.tensor(ref, device=dev)
+    refi = np.stack([orc.dwt_lifting(ref[:, k].copy(), wl.step, wl.norm1, wl.norm2, 20, fw=False) for k in range(2)], axis=1)
+    _strict_then_fast(lambda: wb.idwtc(yg, wl)[:, cols], refi, 1e-5)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("wname", ["haar", "db2", "db4", "db6", "sym8", "db10"])
 def test_onepass_fir3d_vs_oracle(dev, mode, dtype, wname):
     """One-pass marching 3-D level kernels (fir3d_impl.cuh): one launch per level reads the corner once and writes its

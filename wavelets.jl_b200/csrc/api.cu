@@ -522,6 +522,10 @@ static int32_t dispatch_dwt(PassOp<T> &op, void *y, const void *x, const Call &c
     if (!(flags & WB200_FLAG_FORCE_GENERIC) && g.C == 1) {
         int32_t rc = fused_dwt<T>(op, (T *)y, (const T *)x, g, L, fw, workspace, ws_bytes, st, flags);
         if (rc >= 0) return rc;
+        if (lifting && g.ndim == 1) {
+            rc = fused_lift1d<T>(op, (T *)y, (const T *)x, g, L, fw, workspace, ws_bytes, st);
+            if (rc >= 0) return rc;
+        }
     }
     // 2-D lifting: fused level kernels for the large levels, then the pyramid-tail kernel (or, for shapes it does not
     // take, the generic passes) for the small remainder

@@ -113,6 +113,8 @@ template <typename T, int F_, int TI_, int PP_, int NG_, int SI_> struct Cfg {
     static constexpr int STAGE_I = 2 * KR * PIN_I;
     static constexpr int SBUF_I = 2 * KR * PS1;
     static constexpr size_t SMEM_I = (size_t)(2 * STAGE_I + 2 * SBUF_I) * sizeof(T);
+    static constexpr int MINB_F = NT_F <= 224 ? 3 : (NT_F <= 352 ? 2 : 1);      // resident CTAs the register budget is sized for
+    static constexpr int MINB_I = NT_I <= 224 ? 3 : (NT_I <= 352 ? 2 : 1);
     static_assert(F % 2 == 0 && F >= 2, "even filter length");
     static_assert(TIp % SI == 0 && SI % V == 0 && NSEG % 4 == 0, "dim-1 tasks: whole vectors, four segments per warp row group");
     static_assert(TO % 8 == 0, "dim-1 tasks take rows in groups of eight");
@@ -123,7 +125,7 @@ template <typename T, int F_, int TI_, int PP_, int NG_, int SI_> struct Cfg {
 // forward level
 // ===================================================================================================
 template <typename T, int F, bool STRICT, class C>
-__global__ void __launch_bounds__(C::NT_F, 1)
+__global__ void __launch_bounds__(C::NT_F, C::MINB_F)
 k_fir3d_fwd(const T *__restrict__ src, int64_t ld_s, int64_t ps_s, int64_t bs_s,
             T *__restrict__ ll, int64_t ld_ll, int64_t ps_ll, int64_t bs_ll,
             T *__restrict__ yd, int64_t ld_y, int64_t ps_y, int64_t bs_y,
@@ -274,7 +276,7 @@ k_fir3d_fwd(const T *__restrict__ src, int64_t ld_s, int64_t ps_s, int64_t bs_s,
 // inverse level
 // ===================================================================================================
 template <typename T, int F, bool STRICT, class C>
-__global__ void __launch_bounds__(C::NT_I, 1)
+__global__ void __launch_bounds__(C::NT_I, C::MINB_I)
 k_fir3d_inv(const T *__restrict__ ll, int64_t ld_ll, int64_t ps_ll, int64_t bs_ll,
             const T *__restrict__ xd, int64_t ld_x, int64_t ps_x, int64_t bs_x,
             T *__restrict__ dst, int64_t ld_d, int64_t ps_d, int64_t bs_d,
@@ -445,14 +447,17 @@ k_fir3d_inv(const T *__restrict__ ll, int64_t ld_ll, int64_t ps_ll, int64_t bs_l
 // ===================================================================================================
 // host side
 // ===================================================================================================
-// configuration per element type and filter length: Float32 with up to 12 taps keeps four positions per thread (ring of
-// 4 F registers); longer filters and Float64 keep two
-template <typename T, int F> struct Pick {
+// configuration per element type, filter length and direction.  Float32 with up to 12 taps keeps four positions per thread
+// (ring of 4 F registers) on a 64 x 16 tile, two CTAs per SM; longer filters and Float64 keep two positions.  The dim-1
+// synthesis of the inverse takes 8-pair tasks (fewer 16-byte window loads per output), the analysis 4-pair tasks.
+// r02 sweep on 512^3 db6 (profiles/r02_fir3d_tile_sweep.md): 128 x 16 one CTA/SM 0.603 / 0.596 ms (forward / inverse, L = 3),
+// 128 x 8 0.583 / 0.666, 64 x 16 0.577 / 0.551, 64 x 8 0.72 / 0.72, 64 x 16 with 8-pair tasks 0.607 (spills) / 0.535.
+template <typename T, int F, bool FW> struct Pick {
     static constexpr bool WIDE = sizeof(T) == 4 && F <= 12;
-    static constexpr int TI = sizeof(T) == 4 ? 128 : 64;
+    static constexpr int TI = WIDE ? 64 : (sizeof(T) == 4 ? 128 : 64);
     static constexpr int PP = WIDE ? 2 : 1;
     static constexpr int NG = 4;
-    static constexpr int SI = 4;
+    static constexpr int SI = (WIDE && !FW) ? 8 : 4;
     using type = Cfg<T, F, TI, PP, NG, SI>;
 };
 
@@ -482,7 +487,7 @@ template <typename T, int F, bool STRICT>
 static int32_t launch_fwd(const T *src, int64_t ld_s, int64_t ps_s, int64_t bs_s, T *ll, int64_t ld_ll, int64_t ps_ll, int64_t bs_ll,
                           T *y, int64_t ld_y, int64_t ps_y, int64_t bs_y, int nI, int nJ, int nK, int64_t B,
                           const FirCoefs<T, F> &fc, cudaStream_t st) {
-    using C = typename Pick<T, F>::type;
+    using C = typename Pick<T, F, true>::type;
     const int tilesI = nI / C::TI, tilesK = nK / C::TO;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
@@ -504,7 +509,7 @@ template <typename T, int F, bool STRICT>
 static int32_t launch_inv(const T *ll, int64_t ld_ll, int64_t ps_ll, int64_t bs_ll, const T *x, int64_t ld_x, int64_t ps_x, int64_t bs_x,
                           T *dst, int64_t ld_d, int64_t ps_d, int64_t bs_d, int nI, int nJ, int nK, int64_t B,
                           const FirCoefs<T, F> &fc, cudaStream_t st) {
-    using C = typename Pick<T, F>::type;
+    using C = typename Pick<T, F, false>::type;
     const int tilesI = nI / C::TI, tilesJ = nJ / C::TO;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
@@ -525,7 +530,8 @@ static int32_t launch_inv(const T *ll, int64_t ld_ll, int64_t ps_ll, int64_t bs_
 
 // a corner (nI, nJ, nK) is served when every dimension is whole tiles and 16-byte granular
 template <typename T, int F> static bool corner_ok(int64_t nI, int64_t nJ, int64_t nK) {
-    using C = typename Pick<T, F>::type;
+    using C = typename Pick<T, F, true>::type;
+    static_assert(C::TI == Pick<T, F, false>::type::TI && C::TO == Pick<T, F, false>::type::TO, "both directions tile alike");
     constexpr int V = C::V;
     return nI % C::TI == 0 && nJ % C::TO == 0 && nK % C::TO == 0 && (nI / 2) % V == 0 && nI >= C::TI && nJ >= C::TO && nK >= C::TO &&
            nJ >= F && nK >= F && nI < (1 << 30) && nJ < (1 << 30) && nK < (1 << 30);

@@ -14,6 +14,11 @@ int32_t fused_dwt(const PassOp<T> &op, T *y, const T *x, const ArrayGeom &g, int
 // Device scratch the fused path needs for this shape (0 when it does not apply).
 size_t fused_workspace_bytes(const ArrayGeom &g, int esize, int L, bool lifting, bool inplace, uint32_t flags);
 
+// ---- fused multi-level 1-D lifting for batches of contiguous columns (lift1d.cu); same return contract as fused_dwt ----
+template <typename T>
+int32_t fused_lift1d(const PassOp<T> &op, T *y, const T *x, const ArrayGeom &g, int L, bool fw,
+                     void *workspace, size_t ws_bytes, cudaStream_t st);
+
 // ---- 2-D lifting levels (fused2d.cu) ----------------------------------------------------------------------
 // Number of leading levels (1..Lf) the fused 2-D lifting kernels take for this call (0: none).
 template <typename T> int fused2d_levels(const PassOp<T> &op, const ArrayGeom &g, int L, bool fw);
