@@ -10,7 +10,7 @@ import wavelets_b200 as wb
 from wavelets_b200 import _lib
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--kind", default="filter1d", choices=["filter1d", "lift2d", "filter2d", "wpt", "filter3d", "modwt"])
+ap.add_argument("--kind", default="filter1d", choices=["filter1d", "lift1d", "lift2d", "filter2d", "wpt", "filter3d", "modwt"])
 ap.add_argument("--dtype", default="f32")
 ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--n", type=int, default=0)
@@ -25,6 +25,12 @@ wb.set_strict_fp(bool(a.strict))
 if a.kind == "filter1d":
     n = a.n or (1 << 20)
     wt = wb.wavelet(getattr(wb.WT, a.wavelet or "db4"))
+    x = torch.randn((a.batch, n), dtype=tdt, device=dev).t()
+    for _ in range(a.reps):
+        y = wb.dwtc(x, wt, a.levels or None); xr = wb.idwtc(y, wt, a.levels or None)
+elif a.kind == "lift1d":
+    n = a.n or (1 << 20)
+    wt = wb.wavelet(wb.WT.cdf97, wb.WT.Lifting)
     x = torch.randn((a.batch, n), dtype=tdt, device=dev).t()
     for _ in range(a.reps):
         y = wb.dwtc(x, wt, a.levels or None); xr = wb.idwtc(y, wt, a.levels or None)

@@ -88,7 +88,7 @@ __device__ __forceinline__ int wrapm(int v, int n) { v %= n; return v < 0 ? v + 
 // local level l go to the d_{lvl0+l} band of y (y + col*n0 + (n0 >> (lvl0+l))); the level-K approximation goes to
 // dst_a + col*dst_a_stride (y itself when no level remains, else the next stage's scratch).
 template <typename T, class S, bool STRICT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_lift1d_ana(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, int64_t n0, int lvl0,
              T *__restrict__ dst_a, int64_t dst_a_stride, const __grid_constant__ LiftCoefs<T> lc,
              const __grid_constant__ AnaPlanL pl) {
@@ -115,6 +115,12 @@ k_lift1d_ana(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, i
     __syncthreads();
     mbar_wait(bar, 0);
 
+    // per-warp staging of the detail outputs: a lane's segment is SEG consecutive coefficients, so direct stores would touch
+    // every 32-byte sector of the warp's 32*SEG-element run three times (ncu: 3x excessive L2 sectors, profiles/r02c_lift1d_f32.md);
+    // the warp parks the run in shared memory and writes it out as whole 16-byte pieces, lane after lane
+    constexpr int V = Geo<T>::V;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T *wst = bufB + ((((pl.tile >> 1) + 2 * pl.E[1] + 2 * NP + 3) & ~3)) + warp * (32 * SEG);
     const T *in = bufA;
     T *out = bufB;
     for (int l = 1; l <= pl.K; ++l) {
@@ -128,29 +134,39 @@ k_lift1d_ana(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, i
         T *dsta = dst_a + col * dst_a_stride + sl;
         // `in` starts HM pairs before the first computed pair
         const int g00 = sl - El - HM;
-        for (int q = threadIdx.x; q * SEG < ncomp; q += blockDim.x) {
-            T w[2 * NP];
-            ldw<T, 2 * NP>(w, in + 2 * q * SEG);
-            T sv[NP], dv[NP];
+        for (int qb = warp * 32; qb * SEG < ncomp; qb += blockDim.x) {      // warp-uniform trip count
+            const int q = qb + lane;
+            if (q * SEG < ncomp) {
+                T w[2 * NP];
+                ldw<T, 2 * NP>(w, in + 2 * q * SEG);
+                T sv[NP], dv[NP];
 #pragma unroll
-            for (int pp = 0; pp < NP; ++pp) { sv[pp] = w[2 * pp]; dv[pp] = w[2 * pp + 1]; }
-            int g0 = g00 + q * SEG;
-            if (edge) g0 = wrapm(g0, half);
-            lift_regs<T, S, STRICT, NP>(sv, dv, lc, g0, half, edge);
+                for (int pp = 0; pp < NP; ++pp) { sv[pp] = w[2 * pp]; dv[pp] = w[2 * pp + 1]; }
+                int g0 = g00 + q * SEG;
+                if (edge) g0 = wrapm(g0, half);
+                lift_regs<T, S, STRICT, NP>(sv, dv, lc, g0, half, edge);
 #pragma unroll
-            for (int pp = 0; pp < SEG; pp += G) {
-                const int p = q * SEG + pp;             // computed-range index of this piece
-                if (p < ncomp) {
+                for (int pp = 0; pp < SEG; pp += G) {
+                    const int p = q * SEG + pp;         // computed-range index of this piece
                     T os[G], od[G];
 #pragma unroll
                     for (int e = 0; e < G; ++e) { os[e] = fp::mul(sv[HM + pp + e], lc.n1); od[e] = fp::mul(dv[HM + pp + e], lc.n2); }
-                    const int po = p - El;              // owned-range index
-                    const bool own = po >= 0 && po < Tl;
-                    if (!last) st8(out + p, os);
-                    else if (own) st8_cs(dsta + po, os);
-                    if (own) st8_cs(dband + po, od);
+                    st8(wst + lane * SEG + pp, od);
+                    if (p < ncomp) {
+                        const int po = p - El;          // owned-range index
+                        if (!last) st8(out + p, os);
+                        else if (po >= 0 && po < Tl) st8_cs(dsta + po, os);
+                    }
                 }
             }
+            __syncwarp();
+#pragma unroll
+            for (int i = lane; i < 32 * SEG / V; i += 32) {
+                const int p = qb * SEG + i * V;
+                const int po = p - El;
+                if (p < ncomp && po >= 0 && po < Tl) st16v_cs(dband + po, wst + i * V);
+            }
+            __syncwarp();
         }
         if (!last) {
             __syncthreads();
@@ -165,7 +181,7 @@ k_lift1d_ana(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, i
 // Produces a_{lvl0} of a column (ncur = n0 >> lvl0 samples, to dst + col*dst_stride: y when lvl0 == 0) from a_{lvl0+K}
 // (asrc + col*asrc_stride) and the detail bands d_{lvl0+K} .. d_{lvl0+1} of x.
 template <typename T, class S, bool STRICT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_lift1d_syn(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restrict__ x, int64_t n0, int lvl0,
              T *__restrict__ dst, int64_t dst_stride, const __grid_constant__ LiftCoefs<T> lc,
              const __grid_constant__ SynPlanL pl) {
@@ -196,6 +212,7 @@ k_lift1d_syn(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restric
     }
     __syncthreads();
 
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const T *abuf = sm + pl.aoff;
     for (int l = K; l >= 1; --l) {
         mbar_wait(bar + l, 0);
@@ -209,25 +226,28 @@ k_lift1d_syn(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restric
         const T *dbuf = sm + pl.doff[l];
         T *obuf = sm + (((l - 1) & 1) ? pl.poff : pl.qoff);
         T *og = dst + col * dst_stride + s;
-        for (int q = threadIdx.x; q * SEG < ncomp; q += blockDim.x) {
-            T wa[NW], wd[NW];
-            ldw<T, NW>(wa, abuf + woff + q * SEG);
-            ldw<T, NW>(wd, dbuf + woff + q * SEG);
-            T sv[NP], dv[NP];
+        for (int qb = warp * 32; qb * SEG < ncomp; qb += blockDim.x) {      // warp-uniform trip count
+            const int q = qb + lane;
+            if (q * SEG < ncomp) {
+                T wa[NW], wd[NW];
+                ldw<T, NW>(wa, abuf + woff + q * SEG);
+                ldw<T, NW>(wd, dbuf + woff + q * SEG);
+                T sv[NP], dv[NP];
 #pragma unroll
-            for (int pp = 0; pp < NP; ++pp) { sv[pp] = fp::mul(wa[pp + 4 - HM], lc.n1); dv[pp] = fp::mul(wd[pp + 4 - HM], lc.n2); }
-            int g0 = sl + ulo + q * SEG - HM;
-            if (edge) g0 = wrapm(g0, half);
-            lift_regs<T, S, STRICT, NP>(sv, dv, lc, g0, half, edge);
+                for (int pp = 0; pp < NP; ++pp) { sv[pp] = fp::mul(wa[pp + 4 - HM], lc.n1); dv[pp] = fp::mul(wd[pp + 4 - HM], lc.n2); }
+                int g0 = sl + ulo + q * SEG - HM;
+                if (edge) g0 = wrapm(g0, half);
+                lift_regs<T, S, STRICT, NP>(sv, dv, lc, g0, half, edge);
 #pragma unroll
-            for (int pp = 0; pp < SEG; pp += V / 2) {
-                const int u = q * SEG + pp;             // computed-range index of the first pair of this 16-byte piece
-                if (u < ncomp) {
+                for (int pp = 0; pp < SEG; pp += V / 2) {
+                    const int u = q * SEG + pp;         // computed-range index of the first pair of this 16-byte piece
                     T o[V];
 #pragma unroll
                     for (int e = 0; e < V / 2; ++e) { o[2 * e] = sv[HM + pp + e]; o[2 * e + 1] = dv[HM + pp + e]; }
-                    if (l > 1) st16v(obuf + 2 * u, o);   // content starts at sample 2 * ulo = -8
-                    else       st16v_cs(og + 2 * u, o);
+                    if (u < ncomp) {
+                        if (l > 1) st16v(obuf + 2 * u, o);                  // content starts at sample 2 * ulo = -8
+                        else       st16v_cs(og + 2 * u, o);                 // (a per-warp staged, lane-contiguous copy-out measured
+                    }                                                       //  slower here: 4.3 vs 5.0 TB/s, r02 sweep)
                 }
             }
         }
@@ -351,13 +371,15 @@ struct PlanL {
 // (forward), the deepest level keeps at least 16 pairs per tile, a line holds at least two tiles (a wrapped TMA piece never
 // overlaps its tile).
 template <typename T> static bool plan_stage(int64_t cur, int levels, int HM, bool fw, int &K, int &tile_out) {
-    int64_t tile = env_l(sizeof(T) == 4 ? "WB200_LIFT1D_TILE_F32" : "WB200_LIFT1D_TILE_F64", sizeof(T) == 4 ? 8192 : 4096);
-    if (!fw) tile = env_l(sizeof(T) == 4 ? "WB200_LIFT1D_TILE_F32_INV" : "WB200_LIFT1D_TILE_F64_INV", (int)tile);
+    // defaults from the r02 sweep (tools/sweep_lift1d.py, profiles/r02_lift1d_sweep.md): small tiles, four levels per stage --
+    // a CTA is a chain of dependent levels, so many small resident CTAs hide each other's barriers and TMA waits
+    int64_t tile = fw ? env_l(sizeof(T) == 4 ? "WB200_LIFT1D_TILE_F32" : "WB200_LIFT1D_TILE_F64", sizeof(T) == 4 ? 4096 : 2048)
+                      : env_l(sizeof(T) == 4 ? "WB200_LIFT1D_TILE_F32_INV" : "WB200_LIFT1D_TILE_F64_INV", sizeof(T) == 4 ? 2048 : 1024);
     const int64_t p2 = cur & (-cur);
     while (tile > p2) tile >>= 1;
     while (tile > cur / 2) tile >>= 1;
     if (tile < 256 || (cur * (int64_t)sizeof(T)) % 16 != 0) return false;
-    const int kmax = env_l("WB200_LIFT1D_KMAX", 6);
+    const int kmax = env_l("WB200_LIFT1D_KMAX", 4);
     K = levels < kmax ? levels : kmax;
     if (K > MAXK1) K = MAXK1;
     while (K >= 1 && ((tile >> K) < 16 || (fw && 2 * HM * ((1 << K) - 1) > tile / 8))) --K;
@@ -387,15 +409,27 @@ template <typename T> static PlanL plan_l(int64_t n, int L, int HM, bool fw) {
     p.ok = true;
     return p;
 }
+// threads per CTA: the level-1 segment count of a tile spread over whole rounds (a 256-thread CTA left a third of its lanes
+// idle on the 342 level-1 segments of an 8192-sample synthesis tile)
+static int block_for(int segments, const char *envname) {
+    const int forced = env_l(envname, 0);
+    if (forced >= 32 && forced <= 512) return forced & ~31;
+    int rounds = (segments + 95) / 96;                     // ~96 threads per CTA (r02 sweep)
+    if (rounds < 1) rounds = 1;
+    int nt = ((segments + rounds - 1) / rounds + 31) & ~31;
+    if (nt < 64) nt = 64;
+    if (nt > 512) nt = 512;
+    return nt;
+}
 template <typename T> static void make_ana(AnaPlanL &pl, const StageL &sg, int HM) {
     pl.K = sg.K; pl.tile = sg.tile;
     pl.E[sg.K] = 0;
     for (int l = sg.K; l >= 1; --l) pl.E[l - 1] = 2 * (pl.E[l] + HM);
 }
-template <typename T, int NPA> static size_t ana_smem(const AnaPlanL &pl) {
+template <typename T, int NPA> static size_t ana_smem(const AnaPlanL &pl, int nt) {
     const size_t a = ((size_t)pl.tile + 2 * pl.E[0] + 2 * NPA + 3) & ~(size_t)3;
     const size_t b = ((size_t)(pl.tile >> 1) + 2 * pl.E[1] + 2 * NPA + 3) & ~(size_t)3;
-    return 128 + (a + b) * sizeof(T);
+    return 128 + (a + b + (size_t)nt * Geo<T>::SEG_A) * sizeof(T);
 }
 template <typename T> static size_t make_syn(SynPlanL &pl, const StageL &sg) {
     constexpr int SEG = Geo<T>::SEG_S;
@@ -503,7 +537,8 @@ static int32_t run_l1(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t 
             const StageL &sg = p.st[i];
             AnaPlanL pl;
             make_ana<T>(pl, sg, HM);
-            const size_t smem = ana_smem<T, Geo<T>::SEG_A + 2 * HM>(pl);
+            const int nt = block_for(((sg.tile >> 1) + 2 * pl.E[1] + Geo<T>::SEG_A - 1) / Geo<T>::SEG_A, "WB200_LIFT1D_NT");
+            const size_t smem = ana_smem<T, Geo<T>::SEG_A + 2 * HM>(pl, nt);
             auto kern = k_lift1d_ana<T, SF, STRICT>;
             if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
                 (void)cudaGetLastError(); set_error("cudaFuncSetAttribute(k_lift1d_ana) failed"); return WB200_ECUDA;
@@ -517,7 +552,7 @@ static int32_t run_l1(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t 
             dim3 grid((unsigned)(ncur / sg.tile), (unsigned)B);
             {
                 LaunchScope scope("fused_lift1d_ana", st);
-                kern<<<grid, 256, smem, st>>>(src, sstride, y, n, sg.lv0, dsta, dstride, lc, pl);
+                kern<<<grid, nt, smem, st>>>(src, sstride, y, n, sg.lv0, dsta, dstride, lc, pl);
             }
             if (!check_launch("fused_lift1d_ana")) return WB200_ECUDA;
         }
@@ -554,6 +589,7 @@ static int32_t run_l1(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t 
     for (int i = ns - 1; i >= 0; --i) {
         const StageL &sg = p.st[i];
         SynPlanL pl;
+        const int nt = block_for(((sg.tile >> 1) + Geo<T>::SEG_S - 1) / Geo<T>::SEG_S, "WB200_LIFT1D_NT_INV");
         const size_t smem = make_syn<T>(pl, sg);
         auto kern = k_lift1d_syn<T, SI_, STRICT>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -568,7 +604,7 @@ static int32_t run_l1(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t 
         dim3 grid((unsigned)(ncur / sg.tile), (unsigned)B);
         {
             LaunchScope scope("fused_lift1d_syn", st);
-            kern<<<grid, 256, smem, st>>>(asrc, astride, x, n, sg.lv0, dst, dstride, lc, pl);
+            kern<<<grid, nt, smem, st>>>(asrc, astride, x, n, sg.lv0, dst, dstride, lc, pl);
         }
         if (!check_launch("fused_lift1d_syn")) return WB200_ECUDA;
     }
