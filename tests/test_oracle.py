@@ -366,6 +366,54 @@ def test_noisest_and_denoise_properties():
         orc.denoise(rng(8).standard_normal((16, 32)), wt, 2)
 
 
+def test_denoise_TI_vs_independent_numpy_statement():
+    """Translation-invariant denoising (denoising.jl:33-64) restated with numpy only around the golden-pinned transform:
+    the average over all spins of unshift(idwt(threshold(dwt(shift(x))))), np.roll playing circshift, shifts 0 .. nspin-1 per
+    dimension in CartesianIndices order (first dimension fastest), sum accumulated in that order, then * (1 / pns)."""
+    wt = wavelet(WT.sym5)
+    for shape, nspin, L in (((64,), (5,), 3), ((16, 16), (3, 2), 2), ((8, 8, 8), (2, 2, 2), 1)):
+        x = rng(sum(shape)).standard_normal(shape)
+        sig = orc.noisest(x, wt)
+        t = sig * np.sqrt(2 * np.log(shape[0]))
+        acc = np.zeros(shape)
+        import itertools
+        for sh in itertools.product(*[range(k) for k in reversed(nspin)]):
+            sh = tuple(reversed(sh))                                  # first dimension fastest
+            z = np.roll(x, sh, axis=tuple(range(len(shape))))
+            c = _np_threshold(orc.dwt_filter(z, wt.qmf, L), "hard", t)
+            z = orc.dwt_filter(c, wt.qmf, L, fw=False)
+            acc = acc + np.roll(z, tuple(-v for v in sh), axis=tuple(range(len(shape))))
+        ref = acc * (1 / int(np.prod(nspin)))
+        got = orc.denoise(x, wt, L, TI=True, nspin=nspin if len(nspin) > 1 else nspin[0])
+        assert np.array_equal(got, ref), np.max(np.abs(got - ref))
+
+
+def _brute_best_cost(x, qmf, nrm, depth_left):
+    """Cheapest additive Shannon cost over EVERY admissible packet tree below this node (exhaustive recursion)."""
+    s = (x / nrm) ** 2
+    own = float(np.sum(np.where(s > 0, -s * np.log(np.where(s > 0, s, 1.0)), 0.0)))
+    if depth_left == 0 or len(x) < 2:
+        return own
+    y = orc.dwt_filter(x, qmf, 1)
+    h = len(x) // 2
+    return min(own, _brute_best_cost(y[:h], qmf, nrm, depth_left - 1) + _brute_best_cost(y[h:], qmf, nrm, depth_left - 1))
+
+
+@pytest.mark.parametrize("wname", ["haar", "db4"])
+def test_bestbasistree_is_the_exhaustive_optimum(wname):
+    """bestbasistree (entropy.jl:46-108) against an exhaustive search over all packet trees: the chosen basis attains the
+    minimum additive entropy, on the reference's test signal (a sine, test/threshold.jl:24) and on noise."""
+    wt = wavelet(getattr(WT, wname))
+    n = 64
+    for x in (np.sin(4 * np.linspace(0, 2 * np.pi - np.finfo(float).eps, n)), rng(12).standard_normal(n)):
+        full = wb.maketree(n, None, "full")
+        best, bf, af = orc.bestbasistree(x, wt, full)
+        nrm = np.linalg.norm(x)
+        cost_best = orc.coefentropy(orc.wpt_filter(x, wt.qmf, best), "shannon", nrm)
+        brute = _brute_best_cost(x, wt.qmf, nrm, wb.maxtransformlevels(n))
+        assert abs(cost_best - brute) <= 1e-10 * max(1.0, abs(brute)), (cost_best, brute)
+
+
 def test_threshold_biggest_definition():
     for x in (rng(9).standard_normal(200) * 2, np.round(rng(10).standard_normal(300) * 2)):      # the second has many ties
         for m in (0, 1, 17, 150, len(x), len(x) + 5):

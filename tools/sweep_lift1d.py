@@ -25,11 +25,17 @@ def timeit(fn, reps=4):
     return e0.elapsed_time(e1) / reps
 
 
-P = "WB200_LIFT1D_" if kind == "lift" else "WB200_F1D_"
 res = []
-for tile, nt, k in itertools.product((2048, 4096, 8192, 16384), (0, 64, 96, 128, 192, 256, 384), (3, 4, 5, 6)):
-    os.environ[P + "TILE_F32"] = str(tile); os.environ[P + "TILE_F32_INV"] = str(tile)
-    os.environ[P + "NT"] = str(nt); os.environ[P + "NT_INV"] = str(nt); os.environ[P + "KMAX"] = str(k)
+grid = itertools.product((2048, 4096, 8192, 16384), (0, 64, 96, 128, 192, 256, 384), (3, 4, 5, 6)) if kind == "lift" else \
+    itertools.product((2048, 4096, 8192, 16384, 32768), (64, 96, 128, 192, 256, 384), (3, 4, 5, 6, 8))
+for tile, nt, k in grid:
+    if kind == "lift":
+        P = "WB200_LIFT1D_"
+        os.environ[P + "TILE_F32"] = str(tile); os.environ[P + "TILE_F32_INV"] = str(tile)
+        os.environ[P + "NT"] = str(nt); os.environ[P + "NT_INV"] = str(nt); os.environ[P + "KMAX"] = str(k)
+    else:
+        os.environ["WB200_TILE_F32"] = str(tile); os.environ["WB200_TILE_F32_INV"] = str(tile)
+        os.environ["WB200_F1D_NT"] = str(nt); os.environ["WB200_F1D_NT_INV"] = str(nt); os.environ["WB200_KMAX"] = str(k)
     f = timeit(lambda: wb.dwtc(x, wl)); i = timeit(lambda: wb.idwtc(y, wl))
     res.append((tile, nt, k, f, i))
     if os.environ.get("SWEEP_VERBOSE"):

@@ -30,7 +30,7 @@ namespace wb {
 // Details of local level l go to the d_{lvl0+l} band of y (y + col*n0 + (n0 >> (lvl0+l))); the level-K
 // approximation goes to dst_a + col*dst_a_stride (y itself when no level remains, else the next stage's scratch).
 template <typename T, int F, bool STRICT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_ana_tiles(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, int64_t n0, int lvl0,
             T *__restrict__ dst_a, int64_t dst_a_stride,
             const __grid_constant__ Taps<T, F> c, const __grid_constant__ AnaPlan pl) {
@@ -186,7 +186,7 @@ k_ana_tail(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, int
 // Stage A'.  Produces a_{lvl0} of a column (ncur = n0 >> lvl0 samples, to dst + col*dst_stride: y when lvl0 == 0)
 // from a_{lvl0+K} (asrc + col*asrc_stride) and the detail bands d_{lvl0+K} .. d_{lvl0+1} of x.
 template <typename T, int F, bool STRICT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_syn_tiles(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restrict__ x, int64_t n0, int lvl0,
             T *__restrict__ dst, int64_t dst_stride,
             const __grid_constant__ Taps<T, F> c, const __grid_constant__ SynPlan pl) {
@@ -389,6 +389,12 @@ template <typename T> static int tile_max(bool fw) {
     return env_int("WB200_TILE_F64", 4096);
 }
 
+// threads per tile CTA (WB200_F1D_NT / WB200_F1D_NT_INV; default 256)
+static int tile_threads(bool fw) {
+    const int v = env_int(fw ? "WB200_F1D_NT" : "WB200_F1D_NT_INV", 256);
+    return (v >= 32 && v <= 512) ? (v & ~31) : 256;
+}
+
 template <int F, int PA> static int ana_halo(int K, int (&H)[MAXK + 1]) {
     using G = FGeom<F, PA>;
     H[K] = 0;
@@ -551,7 +557,7 @@ static int32_t run_fused_1d(const PassOp<T> &op, T *y, const T *x, int64_t n, in
             dim3 grid((unsigned)(ncur / sg.tile), (unsigned)B);
             {
                 LaunchScope scope("fused_ana_tiles", st);
-                kern<<<grid, 256, smem, st>>>(src, sstride, y, n, sg.lv0, dsta, dstride, taps, pl);
+                kern<<<grid, tile_threads(true), smem, st>>>(src, sstride, y, n, sg.lv0, dsta, dstride, taps, pl);
             }
             if (!check_launch("fused_ana_tiles")) { rc = WB200_ECUDA; return finish(); }
         }
@@ -603,7 +609,7 @@ static int32_t run_fused_1d(const PassOp<T> &op, T *y, const T *x, int64_t n, in
             dim3 grid((unsigned)(ncur / sg.tile), (unsigned)B);
             {
                 LaunchScope scope("fused_syn_tiles", st);
-                kern<<<grid, 256, smem, st>>>(asrc, astride, x, n, sg.lv0, dst, dstride, taps, pl);
+                kern<<<grid, tile_threads(false), smem, st>>>(asrc, astride, x, n, sg.lv0, dst, dstride, taps, pl);
             }
             if (!check_launch("fused_syn_tiles")) { rc = WB200_ECUDA; return finish(); }
         }
