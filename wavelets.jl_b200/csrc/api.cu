@@ -405,7 +405,7 @@ static int32_t run_wpt(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t
             const int64_t nodes = (int64_t)1 << (lv - 1);
             bool all = true;
             for (int64_t k = 0; k < nodes; ++k) all = all && tree[(nodes - 1) + k];
-            if (!all || (n >> (lv - 1)) > 4096) break;
+            if (!all || (n >> (lv - 1)) > wpt_subtree_max_samples((int)sizeof(T))) break;
             --lv;
         }
         if (deep - lv >= 2) lv_sub = lv;       // worth a dedicated launch only for two or more levels

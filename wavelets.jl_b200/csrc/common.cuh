@@ -137,6 +137,8 @@ template <typename T>
 int fast_wpt_subtree(const T *S, T *D, int64_t n, int64_t m, int levels, int64_t nodes, int64_t B,
                      const FilterCoefs<T> &fc, bool strict, bool fw, cudaStream_t st);
 
+int wpt_subtree_max_samples(int esize);   // largest packet node the on-chip subtree kernels take (fastpass.cu)
+
 template <typename T> struct PassOp {
     bool lifting;
     bool strict;

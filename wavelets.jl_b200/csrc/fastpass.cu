@@ -228,7 +228,17 @@ k_walk_syn(View<const T> slo, View<const T> shi, View<const T> salt, int64_t thr
 // write of the node.  Sub-node j of level l occupies [j*ml, (j+1)*ml) of the node's span and is replaced in place by
 // [approximation | detail] (natural / Paley order, transforms_filter.jl:337-353).
 // ===================================================================================================
-constexpr int WPT_SUB_MAX = 4096;
+constexpr int WPT_SUB_MAX = 4096;        // default.  r02 sweep (sym8, 2^16, 1024 signals, wpt + iwpt): 4096 -> 2.40 ms, 8192 -> 2.35 ms
+                                         // (one HBM sweep less, three resident CTAs instead of seven), 16384 -> 3.70 ms (one CTA per SM)
+int wpt_subtree_max_samples(int esize) {
+    (void)esize;
+    const char *e = std::getenv("WB200_WPT_SUBMAX");
+    int v = (e && *e) ? std::atoi(e) : WPT_SUB_MAX;
+    if (v > 8192) v = 8192;
+    int p = 2;
+    while (p * 2 <= v) p *= 2;               // a power of two
+    return p;
+}
 
 // The per-level work is FP32-bound (2 F multiply-adds per sample per level), so the shared-memory side has to stay out
 // of the way: a thread computes FOUR consecutive output pairs from register windows filled with conflict-free 16-byte
@@ -569,7 +579,7 @@ static int wpt_sub_F(const T *S, T *D, int64_t n, int m, int levels, int64_t nod
 template <typename T>
 int fast_wpt_subtree(const T *S, T *D, int64_t n, int64_t m, int levels, int64_t nodes, int64_t B,
                      const FilterCoefs<T> &fc, bool strict, bool fw, cudaStream_t st) {
-    if (!env_fast_enabled() || m > WPT_SUB_MAX || m < 2 || levels < 1 || (m % ((int64_t)1 << levels)) != 0) return 0;
+    if (!env_fast_enabled() || m > wpt_subtree_max_samples((int)sizeof(T)) || m < 2 || levels < 1 || (m % ((int64_t)1 << levels)) != 0) return 0;
     switch (fc.F) {
 #define WB_CASE(FF) case FF: return strict ? wpt_sub_F<T, FF, true>(S, D, n, (int)m, levels, nodes, B, fc, fw, st) : wpt_sub_F<T, FF, false>(S, D, n, (int)m, levels, nodes, B, fc, fw, st);
         WB_CASE(2) WB_CASE(4) WB_CASE(6) WB_CASE(8) WB_CASE(10) WB_CASE(12) WB_CASE(14) WB_CASE(16) WB_CASE(18) WB_CASE(20)
