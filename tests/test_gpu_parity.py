@@ -527,6 +527,7 @@ def test_fused_lift2d_vs_oracle(dev, mode, dtype, wname, n, L, B):
 def test_fastpass_nd_filter_vs_oracle(dev, mode, dtype, wname, monkeypatch):
     from wavelets_b200 import _lib
     monkeypatch.setenv("WB200_DISABLE_FIR2D", "1")     # the fused 2-D level kernels would take the square cases
+    monkeypatch.setenv("WB200_DISABLE_FIR3D", "1")     # ... and the one-pass 3-D level kernels the volumes
     wt = wavelet(wavelet_class(wname))
     for shape, L in (((256, 128), 3), ((512, 512), 2), ((64, 64, 64), 2), ((128, 32, 64), 1)):
         x = rng(sum(shape) + L).standard_normal(shape).astype(dtype)

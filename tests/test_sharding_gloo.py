@@ -24,7 +24,7 @@ def _worker(rank, world, port, B, n, out_path):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import wavelets_b200 as wb
-        from wavelets_b200.shard import shard_range, broadcast_descriptor, allreduce_max, allreduce_sum, gather_columns
+        from wavelets_b200.shard import shard_range, broadcast_descriptor, allreduce_max, allreduce_sum, gather_columns, scatter_columns
         from oracle import oracle as orc
         qmf = wb.wavelet(wb.WT.db4).qmf if rank == 0 else None
         qmf = broadcast_descriptor(qmf, src=0)                      # only rank 0 built the descriptor
@@ -35,9 +35,15 @@ def _worker(rank, world, port, B, n, out_path):
         t_max = allreduce_max(t_rank)
         checksum = allreduce_sum(float(np.sum(y_local)))
         full = gather_columns(torch.tensor(np.ascontiguousarray(y_local)), B, dst=0)
+        # the batch starting on rank 0 only: scatter (batch-major storage = column-major (n, B)), transform, gather
+        xb = torch.tensor(np.ascontiguousarray(x.T)) if rank == 0 else None
+        mine = scatter_columns(xb, B, (n,), torch.float64, "cpu", src=0)
+        y2 = orc.dwt_filter_batch(np.ascontiguousarray(mine.numpy().T), 1, qmf, 6)
+        full2 = gather_columns(torch.tensor(np.ascontiguousarray(y2)), B, dst=0)
         if rank == 0:
             ref = orc.dwt_filter_batch(x, 1, qmf, 6)
             ok = (t_max == float(world)) and np.array_equal(full.numpy(), ref) and abs(checksum - ref.sum()) < 1e-9
+            ok = ok and np.array_equal(full2.numpy(), ref)
             open(out_path, "w").write("ok" if ok else "bad")
     finally:
         dist.destroy_process_group()

@@ -899,8 +899,14 @@ int32_t run_host(void *y_host, const void *x_host, int32_t ndim, const int64_t *
     if (y_host == nullptr || x_host == nullptr) { set_error("null host pointer"); return WB200_EARG; }
     if (batch == 0) return WB200_OK;
     const size_t slice_bytes = (size_t)c.g.slice() * c.esize;
-    // chunk of the batch: ~256 MiB per stage keeps three stages in flight without hoarding HBM
-    int64_t cb = (int64_t)((size_t)(256u << 20) / (slice_bytes ? slice_bytes : 1));
+    // chunk of the batch: ~64 MiB per stage (WB200_HOST_CHUNK_MB).  The first chunk's H2D and the last chunk's D2H cannot
+    // overlap anything, so a call pays about two chunk copies of pipeline fill / drain: 256 MiB chunks cost ~10 ms of a
+    // 48 ms call at the 55 GB/s a PCIe 5 x16 link delivers, 64 MiB chunks ~2.5 ms
+    const char *cm = std::getenv("WB200_HOST_CHUNK_MB");
+    size_t chunk_mb = (cm && *cm) ? (size_t)std::atoll(cm) : 64;
+    if (chunk_mb < 1) chunk_mb = 1;
+    if (chunk_mb > 2048) chunk_mb = 2048;
+    int64_t cb = (int64_t)((chunk_mb << 20) / (slice_bytes ? slice_bytes : 1));
     if (cb < 1) cb = 1;
     if (cb > batch) cb = batch;
     if (batch >= 3 && cb > (batch + 2) / 3) cb = (batch + 2) / 3; // at least three chunks when possible

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 from typing import Tuple
 
-__all__ = ["shard_range", "shard_sizes", "broadcast_descriptor", "allreduce_max", "allreduce_sum", "gather_columns"]
+__all__ = ["shard_range", "shard_sizes", "broadcast_descriptor", "allreduce_max", "allreduce_sum", "scatter_columns", "gather_columns"]
 
 
 def shard_sizes(batch: int, world: int):
@@ -49,6 +49,35 @@ def allreduce_max(value: float, device="cpu") -> float:
 def allreduce_sum(value: float, device="cpu") -> float:
     import torch.distributed as dist
     return _allreduce(value, dist.ReduceOp.SUM, device)
+
+
+def scatter_columns(full, batch: int, tail_shape, dtype, device, src: int = 0):
+    """The split itself when the batch starts on ONE rank (optional row): `src` holds `full` with the batch as its
+    LAST (slowest-varying, Julia layout) dimension and sends every other rank its contiguous block of slices as one
+    point-to-point message (NCCL send/recv = a peer copy over NVLink between the GPUs of one box); returns this rank's
+    shard, shape tail_shape + (b_r,), row-major over the reversed dims so that `.permute` gives the column-major view.
+    `full` is laid out (batch, *reversed tail dims) contiguous -- i.e. the storage of a column-major (tail..., batch) array."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    sizes = shard_sizes(batch, world)
+    rev = tuple(reversed(tuple(int(v) for v in tail_shape)))
+    if rank == src:
+        assert full.shape == (batch,) + rev and full.is_contiguous()
+        lo = 0
+        mine = None
+        for r in range(world):
+            part = full[lo:lo + sizes[r]]
+            if r == src:
+                mine = part
+            elif sizes[r]:
+                dist.send(part, dst=r)
+            lo += sizes[r]
+        return mine
+    buf = torch.empty((sizes[rank],) + rev, dtype=dtype, device=device)
+    if sizes[rank]:
+        dist.recv(buf, src=src)
+    return buf
 
 
 def gather_columns(local, batch: int, dst: int = 0):
