@@ -424,6 +424,100 @@ k_lift2d_tail_inv(const T *__restrict__ x, int64_t ld_x, int64_t bs_x, T *__rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// pyramid tail, register edition (the fused shapes, power-of-two corners 4 .. 64): a thread owns one whole LINE of the
+// level's corner, holds it in registers, runs every predict / update step there with the periodic wrap and the
+// interior / boundary distinction resolved at compile time, and writes the line back de-interleaved -- two barriers per
+// level instead of one per lifting step, no strided lattice.  A 64 x 64 corner with six levels took 29 us in the lattice
+// kernel above (one CTA per image: pure latency, which is what a single 4096^2 image -- BASELINE configs[2] as written --
+// pays twice per dwt + idwt pair).
+// ---------------------------------------------------------------------------------------------------
+template <typename T, class S, bool STRICT, int NPAIR>
+__device__ __forceinline__ void lift_line(T (&s)[NPAIR], T (&d)[NPAIR], const LiftCoefs<T> &lc) {
+    using fp = FP<STRICT>;
+#pragma unroll
+    for (int st = 0; st < S::N; ++st) {
+        const int sh = S::sh(st), nc = S::nc(st);
+        const bool pred = S::pred(st) != 0;
+        const int left = sh > 0 ? sh : 0;
+#pragma unroll
+        for (int p = 0; p < NPAIR; ++p) {       // a step reads only the OTHER band: in place
+            T v = pred ? s[p] : d[p];
+            const int i0 = ((p - sh) % NPAIR + NPAIR) % NPAIR, i1 = ((p + 1 - sh) % NPAIR + NPAIR) % NPAIR;
+            const T t0 = pred ? d[i0] : s[i0];
+            if (nc == 1) {
+                v = fp::mac(v, lc.c[st][0], t0);
+            } else {
+                const T t1 = pred ? d[i1] : s[i1];
+                const bool interior = (p >= left) && (p <= NPAIR + sh - nc);
+                if (STRICT && interior) v = fp::add(v, fp::mac(fp::mul(lc.c[st][0], t0), lc.c[st][1], t1));
+                else                    v = fp::mac(fp::mac(v, lc.c[st][0], t0), lc.c[st][1], t1);
+            }
+            if (pred) s[p] = v; else d[p] = v;
+        }
+    }
+}
+// one pass over the NL lines of an NL x NL corner; element k of line `line` sits at base[k * es]
+template <typename T, class S, bool STRICT, bool FW, int NL>
+__device__ __forceinline__ void tailfast_pass(T *A, int P, bool along_j, const LiftCoefs<T> &lc) {
+    using fp = FP<STRICT>;
+    if ((int)threadIdx.x < NL) {
+        constexpr int NPAIR = NL / 2;
+        T s[NPAIR], d[NPAIR];
+        const int es = along_j ? P : 1;
+        T *base = A + (along_j ? (int)threadIdx.x : (int)threadIdx.x * P);
+        if (FW) {
+#pragma unroll
+            for (int p = 0; p < NPAIR; ++p) { s[p] = base[(2 * p) * es]; d[p] = base[(2 * p + 1) * es]; }
+            lift_line<T, S, STRICT, NPAIR>(s, d, lc);
+#pragma unroll
+            for (int p = 0; p < NPAIR; ++p) { base[p * es] = fp::mul(s[p], lc.n1); base[(NPAIR + p) * es] = fp::mul(d[p], lc.n2); }
+        } else {
+#pragma unroll
+            for (int p = 0; p < NPAIR; ++p) { s[p] = fp::mul(base[p * es], lc.n1); d[p] = fp::mul(base[(NPAIR + p) * es], lc.n2); }
+            lift_line<T, S, STRICT, NPAIR>(s, d, lc);
+#pragma unroll
+            for (int p = 0; p < NPAIR; ++p) { base[(2 * p) * es] = s[p]; base[(2 * p + 1) * es] = d[p]; }
+        }
+    }
+    __syncthreads();
+}
+template <typename T, class S, bool STRICT, bool FW, int NL>
+__device__ __forceinline__ void tailfast_level(T *A, int P, const LiftCoefs<T> &lc) {
+    if (FW) { tailfast_pass<T, S, STRICT, true, NL>(A, P, true, lc);  tailfast_pass<T, S, STRICT, true, NL>(A, P, false, lc); }   // dim 2, then dim 1
+    else    { tailfast_pass<T, S, STRICT, false, NL>(A, P, false, lc); tailfast_pass<T, S, STRICT, false, NL>(A, P, true, lc); }  // dim 1, then dim 2
+}
+template <typename T, class S, bool STRICT, bool FW>
+__global__ void __launch_bounds__(256)
+k_lift2d_tailfast(const T *__restrict__ src, int64_t ld_s, int64_t bs_s, T *__restrict__ dst, int64_t ld_d, int64_t bs_d,
+                  int nt, int levels, const __grid_constant__ LiftCoefs<T> lc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *A = reinterpret_cast<T *>(smem_raw);
+    const int P = nt + 1;                                      // odd pitch: a lane per row walks along dim 1 without bank conflicts
+    const T *sb = src + (int64_t)blockIdx.x * bs_s;
+    T *db = dst + (int64_t)blockIdx.x * bs_d;
+    for (int idx = threadIdx.x; idx < nt * nt; idx += blockDim.x) {
+        const int i = idx % nt, j = idx / nt;
+        A[j * P + i] = sb[(int64_t)j * ld_s + i];
+    }
+    __syncthreads();
+    for (int q = 0; q < levels; ++q) {
+        const int l = FW ? q + 1 : levels - q;
+        switch (nt >> (l - 1)) {
+        case 64: tailfast_level<T, S, STRICT, FW, 64>(A, P, lc); break;
+        case 32: tailfast_level<T, S, STRICT, FW, 32>(A, P, lc); break;
+        case 16: tailfast_level<T, S, STRICT, FW, 16>(A, P, lc); break;
+        case 8:  tailfast_level<T, S, STRICT, FW, 8>(A, P, lc); break;
+        case 4:  tailfast_level<T, S, STRICT, FW, 4>(A, P, lc); break;
+        default: tailfast_level<T, S, STRICT, FW, 2>(A, P, lc); break;
+        }
+    }
+    for (int idx = threadIdx.x; idx < nt * nt; idx += blockDim.x) {
+        const int i = idx % nt, j = idx / nt;
+        db[(int64_t)j * ld_d + i] = A[j * P + i];
+    }
+}
+
 // ===================================================================================================
 // host side
 // ===================================================================================================
@@ -491,6 +585,28 @@ bool fused2d_tail_ok(const PassOp<T> &op, const ArrayGeom &g, int64_t nt, int le
 template <typename T>
 int32_t fused2d_tail(const PassOp<T> &op, const T *src, int64_t ld_s, int64_t bs_s, T *dst, int64_t ld_d, int64_t bs_d,
                      int nt, int levels, int64_t B, bool fw, cudaStream_t st) {
+    // register edition for the fused shapes on power-of-two corners
+    const int sid = op.lifting ? shape_id<T>(op.sc, fw) : 0;
+    if (sid != 0 && nt >= 4 && nt <= 64 && (nt & (nt - 1)) == 0 && levels >= 1 && (nt >> levels) >= 1 && !env_int2("WB200_DISABLE_TAILFAST", 0)) {
+        LiftCoefs<T> lc;
+        fill_coefs<T>(lc, op.sc);
+        const size_t sm = (size_t)nt * (nt + 1) * sizeof(T);
+#define WB_TF(SF, SI_)                                                                                               \
+        {                                                                                                            \
+            LaunchScope scope(fw ? "fused_lift2d_tail_fwd" : "fused_lift2d_tail_inv", st);                           \
+            if (fw) { if (op.strict) k_lift2d_tailfast<T, SF, true, true><<<(unsigned)B, 256, sm, st>>>(src, ld_s, bs_s, dst, ld_d, bs_d, nt, levels, lc);   \
+                      else           k_lift2d_tailfast<T, SF, false, true><<<(unsigned)B, 256, sm, st>>>(src, ld_s, bs_s, dst, ld_d, bs_d, nt, levels, lc); } \
+            else    { if (op.strict) k_lift2d_tailfast<T, SI_, true, false><<<(unsigned)B, 256, sm, st>>>(src, ld_s, bs_s, dst, ld_d, bs_d, nt, levels, lc);  \
+                      else           k_lift2d_tailfast<T, SI_, false, false><<<(unsigned)B, 256, sm, st>>>(src, ld_s, bs_s, dst, ld_d, bs_d, nt, levels, lc); } \
+        }
+        switch (sid) {
+        case 1: WB_TF(ShapeCdf97F, ShapeCdf97I) break;
+        case 2: WB_TF(ShapeHaarF, ShapeHaarI) break;
+        default: WB_TF(ShapeDb2F, ShapeDb2I) break;
+        }
+#undef WB_TF
+        return check_launch("fused_lift2d_tail(register edition)") ? WB200_OK : WB200_ECUDA;
+    }
     const size_t smem = (size_t)nt * nt * sizeof(T);
 #define WB_TAIL(KERN, NAME)                                                                                        \
     {                                                                                                              \
