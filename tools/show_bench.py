@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Print the key numbers of a bench.py JSON line.   python tools/show_bench.py gpurun_out/x.json"""
 import json, sys
-d = json.load(open(sys.argv[1]))
+d = json.loads([l for l in open(sys.argv[1]) if l.strip().startswith("{")][-1])      # (NCCL may print its version line first)
 r = d.get("roofline") or {}
 print("value %.0f %s | dominant %s frac %.3f | pair frac %.3f | e2e %s | clocks %s" % (
     d["value"], d["unit"], r.get("kernel"), r.get("frac", 0), d.get("frac_of_hbm_peak_pair") or 0,

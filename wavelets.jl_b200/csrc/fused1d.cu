@@ -409,7 +409,7 @@ template <typename T, int F>
 static Fused1dCfg plan_split(int64_t n, int L, bool fw) {
     Fused1dCfg c;
     const int tmax = tail_max<T>(fw);
-    const int kcap = env_int("WB200_KMAX", MAXK);
+    const int kcap = fw ? env_int("WB200_KMAX", MAXK) : env_int("WB200_KMAX_INV", env_int("WB200_KMAX", MAXK));
     const int halo_div = env_int("WB200_HALO_DIV", 4);        // accept at most tile/halo_div halo samples per tile
     int64_t cur = n;
     int lv = 0;
