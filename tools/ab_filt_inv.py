@@ -7,14 +7,20 @@ import torch
 import wavelets_b200 as wb
 direction = sys.argv[1] if len(sys.argv) > 1 else "inv"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+f64 = len(sys.argv) > 3 and sys.argv[3] == "f64"
 wl = wb.wavelet(wb.WT.db4)
-x = torch.randn((B, 1 << 20), device="cuda").t()
+x = torch.randn((B, 1 << 20), device="cuda", dtype=torch.float64 if f64 else torch.float32).t()
 y = wb.dwtc(x, wl)
-b = 2 * 4 * B * (1 << 20) / 1e9
+b = 2 * x.element_size() * B * (1 << 20) / 1e9
 sfx = "_INV" if direction == "inv" else ""
-KEYS = ["WB200_TILE_F32" + sfx, "WB200_F1D_NT" + sfx, "WB200_KMAX" + sfx, "WB200_TAILMAX_F32" + sfx]
+if f64:
+    KEYS = ["WB200_TILE_F64", "WB200_F1D_NT" + sfx, "WB200_KMAX" + sfx, "WB200_TAILMAX_F64"]
+    grid = ((2048, 96, 4, 2048), (4096, 96, 4, 4096), (2048, 64, 4, 2048), (2048, 128, 4, 2048), (2048, 96, 3, 2048), (2048, 96, 5, 2048), (4096, 128, 5, 4096), (1024, 64, 3, 1024))
+else:
+    KEYS = ["WB200_TILE_F32" + sfx, "WB200_F1D_NT" + sfx, "WB200_KMAX" + sfx, "WB200_TAILMAX_F32" + sfx]
+    grid = ((4096, 96, 4, 4096), (4096, 64, 4, 4096), (4096, 128, 4, 4096), (4096, 96, 3, 4096), (4096, 96, 5, 4096), (4096, 96, 4, 2048), (4096, 96, 4, 8192), (8192, 192, 4, 4096), (2048, 96, 4, 4096))
 cfgs = {"default": {}}
-for tile, nt, k, tm in ((4096, 96, 4, 4096), (2048, 96, 3, 2048), (4096, 128, 4, 4096), (8192, 128, 4, 8192), (8192, 256, 5, 8192), (4096, 96, 4, 16384), (2048, 64, 4, 2048)):
+for tile, nt, k, tm in grid:
     cfgs[f"tile{tile}_nt{nt}_k{k}_tail{tm}"] = dict(zip(KEYS, map(str, (tile, nt, k, tm))))
 fn = (lambda: wb.idwtc(y, wl)) if direction == "inv" else (lambda: wb.dwtc(x, wl))
 def timeit(reps=5):

@@ -3,6 +3,7 @@
 "What proves a Blackwell-native kernel") counted from `cuobjdump -sass` of the built library, next to the `-Xptxas -v`
 resource lines of the same build.     python tools/sass_counts.py > profiles/r02_sass_counts.md
     UBLKCP   = cp.async.bulk (1-D TMA bulk copy)          UTMALDG = cp.async.bulk.tensor (tensor-map TMA load)
+    LDGSTS   = cp.async (16-byte global -> shared, the one-pass 3-D loader: periodic wrap per chunk)
     SYNCS    = mbarrier arrive / try_wait                  LDS.128 / STS.128 = 16-byte shared-memory accesses
     STG.E.128 (+ .EF = evict-first) = 16-byte global stores;   LDG.E.128 = 16-byte global loads;   FFMA / DFMA = the arithmetic"""
 import collections
@@ -14,13 +15,13 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "wavelets.jl_b200", "lib", "libwavelets_b200.so")
-PATS = [("UBLKCP", r"\bUBLKCP"), ("UTMALDG", r"\bUTMALDG"), ("SYNCS", r"\bSYNCS"), ("LDS.128", r"\bLDS\.128"), ("STS.128", r"\bSTS\.128"),
+PATS = [("UBLKCP", r"\bUBLKCP"), ("UTMALDG", r"\bUTMALDG"), ("SYNCS", r"\bSYNCS"), ("LDGSTS", r"\bLDGSTS"), ("LDS.128", r"\bLDS\.128"), ("STS.128", r"\bSTS\.128"),
         ("LDG.E.128", r"\bLDG\.E\.128"), ("STG.E.128", r"\bSTG\.E\.128"), ("STG.E.EF.128", r"\bSTG\.E\.EF\.128"),
         ("STG.E.EF.64", r"\bSTG\.E\.EF\.64"), ("FFMA", r"\bFFMA"), ("DFMA", r"\bDFMA"), ("BAR.SYNC", r"\bBAR\.SYNC")]
 
 
 def family(name):
-    m = re.match(r"(?:void )?(?:wb::)?(?:\(anonymous namespace\)::)?(k_[A-Za-z0-9_]+)", name)
+    m = re.match(r"(?:void )?(?:[A-Za-z0-9_]+::|\(anonymous namespace\)::)*(k_[A-Za-z0-9_]+)", name)
     return m.group(1) if m else name[:40]
 
 
@@ -58,8 +59,8 @@ def main():
     # ptxas -v: registers / shared memory / spills of the headline instantiations
     print("\n## `-Xptxas -v` resource lines (wavelets.jl_b200/lib/obj/*.ptxas.log), headline instantiations\n")
     want = [r"k_ana_tiles<float, 8, false>", r"k_syn_tiles<float, 8, false>", r"k_ana_tiles<double, 8, false>", r"k_syn_tiles<double, 8, false>",
-            r"k_lift1d_\w+<float.*false", r"k_lift2d_fwd_tma<float, wb::ShapeCdf97F, false", r"k_lift2d_inv_tma<float, wb::ShapeCdf97I, false",
-            r"k_lift2d_fwd_tma<float, wb::ShapeFirA<8>, false", r"k_fir3d_\w+<float, 12, false", r"k_wpt_sub_ana<float, 16, false", r"k_wpt_sub_syn<float, 16, false"]
+            r"k_lift1d_(ana|syn)<float, wb::ShapeCdf97\w, false", r"k_lift2d_fwd_tma<float, wb::ShapeCdf97F, false", r"k_lift2d_inv_tma<float, wb::ShapeCdf97I, false",
+            r"k_lift2d_fwd_tma<float, wb::ShapeFirA<8>, false", r"k_fir3d_\w+<float, 12, false", r"k_lift2d_tailfast<float, wb::ShapeCdf97F, false", r"k_wpt_sub_ana<float, 16, false", r"k_wpt_sub_syn<float, 16, false"]
     print("| kernel | registers | spill stores / loads | static smem |")
     print("|---|---|---|---|")
     for log in sorted(glob.glob(os.path.join(ROOT, "wavelets.jl_b200", "lib", "obj", "*.ptxas.log"))):

@@ -377,22 +377,25 @@ struct Fused1dCfg {
     int64_t m = 0;         // tail line length (n >> tail_lv0)
 };
 
-// defaults from the r01 sweep (tools/tune_fused1d.py, profiles/r01_tune_*.log): fewer fused levels (smaller halo) and a
-// larger whole-line tail win once the tails load with TMA
-// (Float32 inverse prefers a longer tile / shorter tail than the forward pass: its per-tile halo is tiny, r01 sweep.)
+// Defaults from the round-2 interleaved A/B (tools/ab_filt_inv.py, profiles/r02_fused1d_ab.md): SMALL tiles, four levels per
+// stage, 96-thread CTAs and a 16 KB whole-line tail.  A tile CTA is a chain of dependent levels (TMA wait, then K x
+// (window loads -> FIR -> stores -> barrier)); many small resident CTAs hide each other's waits better than the 8192 /
+// 16384-sample tiles of 256 threads and up to 8 levels that round 1 tuned one knob at a time (f32 +10 % forward, +16 % inverse;
+// f64 +13 % / +22 %).
 template <typename T> static int tail_max(bool fw) {
-    if (sizeof(T) == 4) return fw ? env_int("WB200_TAILMAX_F32", 32768) : env_int("WB200_TAILMAX_F32_INV", env_int("WB200_TAILMAX_F32", 16384));
-    return env_int("WB200_TAILMAX_F64", 16384);
+    if (sizeof(T) == 4) return fw ? env_int("WB200_TAILMAX_F32", 4096) : env_int("WB200_TAILMAX_F32_INV", env_int("WB200_TAILMAX_F32", 4096));
+    return env_int("WB200_TAILMAX_F64", 2048);
 }
 template <typename T> static int tile_max(bool fw) {
-    if (sizeof(T) == 4) return fw ? env_int("WB200_TILE_F32", 8192) : env_int("WB200_TILE_F32_INV", env_int("WB200_TILE_F32", 16384));
-    return env_int("WB200_TILE_F64", 4096);
+    if (sizeof(T) == 4) return fw ? env_int("WB200_TILE_F32", 4096) : env_int("WB200_TILE_F32_INV", env_int("WB200_TILE_F32", 4096));
+    return env_int("WB200_TILE_F64", 2048);
 }
+constexpr int KMAX_DEFAULT = 4;
 
-// threads per tile CTA (WB200_F1D_NT / WB200_F1D_NT_INV; default 256)
+// threads per tile CTA (WB200_F1D_NT / WB200_F1D_NT_INV)
 static int tile_threads(bool fw) {
-    const int v = env_int(fw ? "WB200_F1D_NT" : "WB200_F1D_NT_INV", 256);
-    return (v >= 32 && v <= 512) ? (v & ~31) : 256;
+    const int v = env_int(fw ? "WB200_F1D_NT" : "WB200_F1D_NT_INV", 96);
+    return (v >= 32 && v <= 512) ? (v & ~31) : 96;
 }
 
 template <int F, int PA> static int ana_halo(int K, int (&H)[MAXK + 1]) {
@@ -409,7 +412,7 @@ template <typename T, int F>
 static Fused1dCfg plan_split(int64_t n, int L, bool fw) {
     Fused1dCfg c;
     const int tmax = tail_max<T>(fw);
-    const int kcap = fw ? env_int("WB200_KMAX", MAXK) : env_int("WB200_KMAX_INV", env_int("WB200_KMAX", MAXK));
+    const int kcap = fw ? env_int("WB200_KMAX", KMAX_DEFAULT) : env_int("WB200_KMAX_INV", env_int("WB200_KMAX", KMAX_DEFAULT));
     const int halo_div = env_int("WB200_HALO_DIV", 4);        // accept at most tile/halo_div halo samples per tile
     int64_t cur = n;
     int lv = 0;
