@@ -19,7 +19,7 @@ namespace wb {
 template <typename T, int F> struct FirTile {
     static constexpr bool SMALL = (sizeof(T) == 8) || (F >= 14);
     // Float32 filters of 10 and 12 taps are built in both configurations (WB200_FIR_SMALL = 0 / 1 overrides the default)
-    static constexpr bool BOTH = (sizeof(T) == 4) && (F == 10 || F == 12);
+    static constexpr bool BOTH = (sizeof(T) == 4) && (F == 8 || F == 10 || F == 12);
 };
 template <typename T, int F, bool FW, bool SMALL>
 using FirCfg = Cfg3<T, std::conditional_t<FW, ShapeFirA<F>, ShapeFirS<F>>, 128, SMALL ? 32 : 64, SMALL ? 8 : 16, SMALL ? 8 : 16>;
