@@ -461,6 +461,24 @@ def test_fused_tiles_vs_oracle(dev, mode, small_tiles, dtype, wname):
         check(xr, orc.dwt_filter_batch(to_np(y), 1, wt.qmf, L, fw=False), mode, L, 4.0)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("wname", ["db11", "coif8", "vaid"])
+def test_fused_tiles_long_even_filters(dev, mode, dtype, wname):
+    """22- and 24-tap filters (db11; coif8 and Vaidyanathan, wt_main.jl:372-436) through the fused 1-D tile kernels with the
+    default tile plan."""
+    from wavelets_b200 import _lib
+    wt = wavelet(wavelet_class(wname))
+    for n, B, L in ((1 << 16, 2, 16), (3 * 8192, 3, 5)):
+        x = rng(n % 977 + B).standard_normal((n, B)).astype(dtype)
+        _lib.lib().wb200_profile_enable(1)
+        y = wb.dwtc(to_gpu(x, dev), wt, L)
+        xr = wb.idwtc(y, wt, L)
+        _lib.lib().wb200_profile_enable(0)
+        assert {"fused_ana_tiles", "fused_syn_tiles"} <= _kernel_names()
+        check(y, orc.dwt_filter_batch(x, 1, wt.qmf, L), mode, L, 4.0)
+        check(xr, orc.dwt_filter_batch(to_np(y), 1, wt.qmf, L, fw=False), mode, L, 4.0)
+
+
 @pytest.mark.parametrize("kmax", [1, 2, 3, 8])
 @pytest.mark.parametrize("wname", ["db4", "db10", "haar"])
 def test_fused_tiles_stage_splits(dev, small_tiles, monkeypatch, kmax, wname):

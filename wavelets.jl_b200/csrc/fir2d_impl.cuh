@@ -18,7 +18,7 @@ namespace wb {
 // resident CTAs per SM
 template <typename T, int F> struct FirTile {
     static constexpr bool SMALL = (sizeof(T) == 8) || (F >= 14);
-    // Float32 filters of 10 and 12 taps are built in both configurations (WB200_FIR_SMALL = 0 / 1 overrides the default)
+    // Float32 filters of 8, 10 and 12 taps are built in both configurations (WB200_FIR_SMALL = 0 / 1 overrides the default)
     static constexpr bool BOTH = (sizeof(T) == 4) && (F == 8 || F == 10 || F == 12);
 };
 template <typename T, int F, bool FW, bool SMALL>
@@ -68,7 +68,9 @@ static int32_t fir_launch_level(const T *a, int64_t lda, int64_t bsa, const T *x
                                 int n, int64_t B, const FirCoefs<T, F> &fc, cudaStream_t st) {
     if constexpr (FirTile<T, F>::BOTH) {
         const char *e = std::getenv("WB200_FIR_SMALL");
-        const bool small = e ? (std::atoi(e) != 0) : FirTile<T, F>::SMALL;
+        // r02 interleaved A/B (tools/ab_fir2d.py, 4096^2 x 64): db4 synthesis 3835 vs 3612 GB/s on the small tile, analysis
+        // 3385 vs 3542; db6 loses on the small tile in both directions
+        const bool small = e ? (std::atoi(e) != 0) : ((F == 8 && !FW) ? true : FirTile<T, F>::SMALL);
         if (small) return fir_launch_cfg<T, F, STRICT, FW, true>(a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, o2, ld2, bs2, n, B, fc, st);
         return fir_launch_cfg<T, F, STRICT, FW, false>(a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, o2, ld2, bs2, n, B, fc, st);
     } else {

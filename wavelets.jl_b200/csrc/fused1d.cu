@@ -626,6 +626,7 @@ static int32_t dispatch_F(const PassOp<T> &op, T *y, const T *x, int64_t n, int6
     switch (op.fc.F) {
 #define WB_CASE(FF) case FF: return run_fused_1d<T, FF, STRICT>(op, y, x, n, B, L, fw, ws, wsb, st);
         WB_CASE(2) WB_CASE(4) WB_CASE(6) WB_CASE(8) WB_CASE(10) WB_CASE(12) WB_CASE(14) WB_CASE(16) WB_CASE(18) WB_CASE(20)
+        WB_CASE(22) WB_CASE(24)                                  // db11, and the 24-tap coif8 / Vaidyanathan filters of wt_main.jl:372-436
 #undef WB_CASE
     default: return -1;
     }
@@ -658,7 +659,7 @@ template <typename T> static size_t fused_ws_T(int64_t n, int64_t B, int L) {
         const bool fw = d != 0;
         one(plan_split<T, 2>(n, L, fw)); one(plan_split<T, 4>(n, L, fw)); one(plan_split<T, 6>(n, L, fw)); one(plan_split<T, 8>(n, L, fw));
         one(plan_split<T, 10>(n, L, fw)); one(plan_split<T, 12>(n, L, fw)); one(plan_split<T, 14>(n, L, fw)); one(plan_split<T, 16>(n, L, fw));
-        one(plan_split<T, 18>(n, L, fw)); one(plan_split<T, 20>(n, L, fw));
+        one(plan_split<T, 18>(n, L, fw)); one(plan_split<T, 20>(n, L, fw)); one(plan_split<T, 22>(n, L, fw)); one(plan_split<T, 24>(n, L, fw));
     }
     return need;
 }
