@@ -52,6 +52,7 @@ struct SynPlanL {
     int doff[MAXK1 + 1];   // element offset of the staged d_l slice (content: pairs [s_l - 8, s_l + T_l + 8))
     int aoff;              // staged a_K slice (same range convention)
     int poff, qoff;        // ping-pong buffers for a_{K-1} .. a_1 (content [s_l - 8, s_l + T_l + 8))
+    int woff;              // per-warp output staging (32 * 2 * SEG elements per warp), or -1: direct 16-byte stores
 };
 
 template <typename T, int N> __device__ __forceinline__ void ldw(T (&w)[N], const T *p) {
@@ -213,6 +214,7 @@ k_lift1d_syn(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restric
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T *wst = sm + (pl.woff >= 0 ? pl.woff : 0) + warp * (32 * 2 * SEG);
     const T *abuf = sm + pl.aoff;
     for (int l = K; l >= 1; --l) {
         mbar_wait(bar + l, 0);
@@ -244,11 +246,18 @@ k_lift1d_syn(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restric
                     T o[V];
 #pragma unroll
                     for (int e = 0; e < V / 2; ++e) { o[2 * e] = sv[HM + pp + e]; o[2 * e + 1] = dv[HM + pp + e]; }
-                    if (u < ncomp) {
-                        if (l > 1) st16v(obuf + 2 * u, o);                  // content starts at sample 2 * ulo = -8
-                        else       st16v_cs(og + 2 * u, o);                 // (a per-warp staged, lane-contiguous copy-out measured
-                    }                                                       //  slower here: 4.3 vs 5.0 TB/s, r02 sweep)
+                    if (l > 1) { if (u < ncomp) st16v(obuf + 2 * u, o); }    // content starts at sample 2 * ulo = -8
+                    else if (pl.woff < 0) { if (u < ncomp) st16v_cs(og + 2 * u, o); }
+                    else st16v(wst + lane * 2 * SEG + 2 * pp, o);
                 }
+            }
+            if (l == 1 && pl.woff >= 0) {   // optional lane-contiguous copy-out through a per-warp staging run (WB200_LIFT1D_INV_STAGED)
+                __syncwarp();
+                for (int i = lane; i < 32 * 2 * SEG / V; i += 32) {
+                    const int idx = 2 * qb * SEG + i * V;                   // sample index inside the tile
+                    if (idx < 2 * ncomp) st16v_cs(og + idx, wst + i * V);
+                }
+                __syncwarp();
             }
         }
         if (l > 1) {
@@ -374,7 +383,7 @@ template <typename T> static bool plan_stage(int64_t cur, int levels, int HM, bo
     // defaults from the r02 sweep (tools/sweep_lift1d.py, profiles/r02_lift1d_sweep.md): small tiles, four levels per stage --
     // a CTA is a chain of dependent levels, so many small resident CTAs hide each other's barriers and TMA waits
     int64_t tile = fw ? env_l(sizeof(T) == 4 ? "WB200_LIFT1D_TILE_F32" : "WB200_LIFT1D_TILE_F64", sizeof(T) == 4 ? 4096 : 2048)
-                      : env_l(sizeof(T) == 4 ? "WB200_LIFT1D_TILE_F32_INV" : "WB200_LIFT1D_TILE_F64_INV", sizeof(T) == 4 ? 2048 : 1024);
+                      : env_l(sizeof(T) == 4 ? "WB200_LIFT1D_TILE_F32_INV" : "WB200_LIFT1D_TILE_F64_INV", sizeof(T) == 4 ? 4096 : 2048);   // interleaved A/B (tools/ab_lift1d.py): 4096 beats 2048 by 11 %
     const int64_t p2 = cur & (-cur);
     while (tile > p2) tile >>= 1;
     while (tile > cur / 2) tile >>= 1;
@@ -431,7 +440,7 @@ template <typename T, int NPA> static size_t ana_smem(const AnaPlanL &pl, int nt
     const size_t b = ((size_t)(pl.tile >> 1) + 2 * pl.E[1] + 2 * NPA + 3) & ~(size_t)3;
     return 128 + (a + b + (size_t)nt * Geo<T>::SEG_A) * sizeof(T);
 }
-template <typename T> static size_t make_syn(SynPlanL &pl, const StageL &sg) {
+template <typename T> static size_t make_syn(SynPlanL &pl, const StageL &sg, int nt) {
     constexpr int SEG = Geo<T>::SEG_S;
     pl.K = sg.K; pl.tile = sg.tile;
     size_t off = 0;
@@ -446,6 +455,8 @@ template <typename T> static size_t make_syn(SynPlanL &pl, const StageL &sg) {
     }
     pl.poff = (int)off; off += psz;
     pl.qoff = (int)off; off += qsz;
+    pl.woff = -1;
+    if (env_l("WB200_LIFT1D_INV_STAGED", 0)) { pl.woff = (int)off; off += (size_t)nt * 2 * SEG; }
     return 128 + off * sizeof(T);
 }
 
@@ -590,7 +601,7 @@ static int32_t run_l1(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t 
         const StageL &sg = p.st[i];
         SynPlanL pl;
         const int nt = block_for(((sg.tile >> 1) + Geo<T>::SEG_S - 1) / Geo<T>::SEG_S, "WB200_LIFT1D_NT_INV");
-        const size_t smem = make_syn<T>(pl, sg);
+        const size_t smem = make_syn<T>(pl, sg, nt);
         auto kern = k_lift1d_syn<T, SI_, STRICT>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             (void)cudaGetLastError(); set_error("cudaFuncSetAttribute(k_lift1d_syn) failed"); return WB200_ECUDA;
