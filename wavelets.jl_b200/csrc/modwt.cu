@@ -576,8 +576,9 @@ k_imodwt_group_v4(const T *__restrict__ vin, int64_t svin, const T *__restrict__
 // ---- host: the group plan ---------------------------------------------------------------------------
 struct MStep { bool fused; int level; MGroup g; };      // fused group, or one level (1-based) through the per-level kernel
 constexpr int MODWT_CAP_BYTES = 36864;                    // one shared-memory buffer of a forward tile (two per CTA)
-constexpr int MODWT_INV_CAP_BYTES = 24576;                // inverse: three per CTA; the smaller tile keeps 3 CTAs per SM resident, which
-                                                          // hides the per-level W loads better (L = 10: 2.23 -> 1.95 ms; sweep in DESIGN.md)
+constexpr int MODWT_INV_CAP_BYTES = 16384;                // inverse: three per CTA; small tiles keep more CTAs per SM resident, which hides the
+                                                          // per-level W loads better (L = 10: 36 K 2.23, 24 K 1.95, 16 K 1.81, 12 K 2.19 ms;
+                                                          // 16 K also wins at L = 5 and L = 20: interleaved A/B, tools/ab_env.py, round 2)
 
 static int modwt_cap_bytes(bool fw) {      // shared-memory bytes of one tile buffer (tuning knob; the plan adapts to it)
     const char *e = std::getenv(fw ? "WB200_MODWT_CAP" : "WB200_MODWT_INV_CAP");
