@@ -893,6 +893,34 @@ def test_denoise_vs_oracle(dev, mode, dtype, kind):
         assert np.array_equal(to_np(a), b)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind", ["hard", "soft", "stein"])
+def test_denoise_threshold_rides_in_the_inverse_loads(dev, dtype, kind, monkeypatch):
+    """1-D filter denoise: threshold!(xt, ...) is applied as an epilogue of the synthesis kernels' staged loads (no separate
+    elementwise launch), bit-identical to the oracle and to the library's own separate-pass route."""
+    from wavelets_b200 import _lib
+    th = {"hard": wb.HardTH(), "soft": wb.SoftTH(), "stein": wb.SteinTH()}[kind]
+    wt = wavelet(WT.sym5)
+    for n, L in ((1 << 16, 6), (3 * 4096, 3), (1024, 10)):        # two tile stages + tail / one stage / tail only
+        x = (_doppler(n) + 0.1 * rng(n % 97).standard_normal(n)).astype(dtype)
+        xg = to_gpu(x, dev)
+        wb.set_strict_fp(True)
+        try:
+            _lib.lib().wb200_profile_enable(1)
+            y = wb.denoise(xg, wt, L=L, dnt=wb.VisuShrink(th, np.sqrt(2 * np.log(n))))
+            _lib.lib().wb200_profile_enable(0)
+            names = _kernel_names()
+            monkeypatch.setenv("WB200_DISABLE_THRESH_EPILOGUE", "1")
+            y2 = wb.denoise(xg, wt, L=L, dnt=wb.VisuShrink(th, np.sqrt(2 * np.log(n))))
+            monkeypatch.delenv("WB200_DISABLE_THRESH_EPILOGUE")
+        finally:
+            wb.set_strict_fp(False)
+        assert "threshold" not in names, names
+        assert torch.equal(y, y2)
+        ref = orc.denoise(x, wt, L, kind=kind)
+        assert np.array_equal(to_np(y), ref), np.max(np.abs(to_np(y) - ref))
+
+
 def test_denoise_defaults_errors_and_scale(dev):
     n = 256
     x0 = _doppler(n)

@@ -629,6 +629,26 @@ static int32_t dispatch_dwt(PassOp<T> &op, void *y, const void *x, const Call &c
     return run_nd<T>(op, (T *)y, xin, g, L, fw, ws);
 }
 
+template <typename T>
+static int32_t idwt_thr_T(void *y, const void *x, int64_t n, int64_t batch, const double *qmf, int32_t flen, int32_t L,
+                          const ThreshEpi &epi, cudaStream_t st, uint32_t flags) {
+    PassOp<T> op;
+    op.lifting = false; op.strict = (flags & WB200_FLAG_STRICT_FP) != 0; op.st = st; op.generic_only = false;
+    op.epi = epi;
+    make_filter<T>(op.fc, qmf, flen);
+    ArrayGeom g;
+    g.C = 1; g.ndim = 1; g.dim[0] = n; g.dim[1] = 1; g.dim[2] = 1; g.batch = batch;
+    return fused_dwt<T>(op, (T *)y, (const T *)x, g, L, false, nullptr, 0, st, flags);     // -1: not a fused shape
+}
+int32_t idwt_filter_thresholded(void *y, const void *x, int64_t n, int64_t batch, const double *qmf, int32_t flen, int32_t L,
+                                int32_t dtype, const ThreshEpi &epi, cudaStream_t st, uint32_t flags) {
+    if ((flags & WB200_FLAG_FORCE_GENERIC) || L < 1 || n < 2 || batch < 1 || y == x || qmf == nullptr || !suffpow2(n, L)) return -1;
+    if (flen < 2 || flen > WB200_MAX_FILTER_LEN || std::getenv("WB200_DISABLE_THRESH_EPILOGUE") != nullptr) return -1;
+    if (dtype == WB200_F64) return idwt_thr_T<double>(y, x, n, batch, qmf, flen, L, epi, st, flags);
+    if (dtype == WB200_F32) return idwt_thr_T<float>(y, x, n, batch, qmf, flen, L, epi, st, flags);
+    return -1;
+}
+
 } // namespace wb
 
 using namespace wb;

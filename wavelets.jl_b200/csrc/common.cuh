@@ -87,6 +87,20 @@ struct LaunchScope {
     ~LaunchScope();
 };
 
+// threshold!(x, TH, t) folded into the LOADS of an inverse transform ("the threshold is an elementwise
+// epilogue that can ride in the idwt load"): kind < 0 = none; t = sigma_dev ? *sigma_dev * tfac : t_host.  Honoured by the
+// fused 1-D filter synthesis kernels only (idwt_filter_thresholded, api.cu, reports when it could not take a call).
+struct ThreshEpi {
+    int kind = -1;
+    double t_host = 0.0, tfac = 1.0;
+    const double *sigma_dev = nullptr;
+};
+
+// inverse 1-D filter-bank transform with the threshold applied to every coefficient as it is staged (api.cu): WB200_OK when
+// the fused kernels took the call, -1 when the shape is not theirs (the caller then thresholds in its own pass)
+int32_t idwt_filter_thresholded(void *y, const void *x, int64_t n, int64_t batch, const double *qmf, int32_t flen, int32_t L,
+                                int32_t dtype, const ThreshEpi &epi, cudaStream_t st, uint32_t flags);
+
 template <typename T> constexpr int dtype_of();
 template <> constexpr int dtype_of<float>() { return WB200_F32; }
 template <> constexpr int dtype_of<double>() { return WB200_F64; }
@@ -140,6 +154,7 @@ int fast_wpt_subtree(const T *S, T *D, int64_t n, int64_t m, int levels, int64_t
 int wpt_subtree_max_samples(int esize);   // largest packet node the on-chip subtree kernels take (fastpass.cu)
 
 template <typename T> struct PassOp {
+    ThreshEpi epi;
     bool lifting;
     bool strict;
     cudaStream_t st;

@@ -21,6 +21,7 @@
 // Arithmetic is the reference's (filtdown!/filtup! closed forms) in the reference's summation
 // order; STRICT keeps multiply and add separately rounded (bit-identical to the CPU path), otherwise FMA.
 #include "fused1d_dev.cuh"
+#include "thresh_dev.cuh"
 
 #include <cstdlib>
 
@@ -189,7 +190,8 @@ template <typename T, int F, bool STRICT>
 __global__ void __launch_bounds__(512)
 k_syn_tiles(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restrict__ x, int64_t n0, int lvl0,
             T *__restrict__ dst, int64_t dst_stride,
-            const __grid_constant__ Taps<T, F> c, const __grid_constant__ SynPlan pl) {
+            const __grid_constant__ Taps<T, F> c, const __grid_constant__ SynPlan pl,
+            const __grid_constant__ ThreshEpi epi, int thr_a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     T *sm = reinterpret_cast<T *>(smem_raw + 128);
@@ -215,8 +217,22 @@ k_syn_tiles(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restrict
     __syncthreads();
 
     const T *abuf = sm + pl.aoff;
+    const double tthr = epi.kind >= 0 ? (epi.sigma_dev ? __dmul_rn(*epi.sigma_dev, epi.tfac) : epi.t_host) : 0.0;
     for (int l = K; l >= 1; --l) {
         mbar_wait(bar + l, 0);
+        if (epi.kind >= 0) {
+            // threshold!(xt, TH, t) as a load epilogue (denoising.jl:44, 69): every staged coefficient of d_l (halo included:
+            // it feeds this tile's outputs) and, where the approximation is x's own a_L, that slice too
+            T *dst_d = sm + pl.doff[l];
+            const int nd = pl.dhi[l] - pl.dlo[l];
+            for (int i = threadIdx.x; i < nd; i += blockDim.x) dst_d[i] = thresh_apply<T>(dst_d[i], epi.kind, tthr);
+            if (l == K && thr_a) {
+                T *dst_a = sm + pl.aoff;
+                const int na = pl.rhi[K] - pl.rlo[K];
+                for (int i = threadIdx.x; i < na; i += blockDim.x) dst_a[i] = thresh_apply<T>(dst_a[i], epi.kind, tthr);
+            }
+            __syncthreads();
+        }
         // produce the approximation one level up on [s_{l-1} + rlo[l-1], s_{l-1} + rhi[l-1])
         const int npairs = (pl.rhi[l - 1] - pl.rlo[l - 1]) >> 1;           // output pairs = values of u
         const int oa = (pl.rlo[l - 1] >> 1) - pl.rlo[l];                   // index of a[u_first] inside abuf
@@ -255,7 +271,7 @@ template <typename T, int F> struct SynTailGeom {
 template <typename T, int F, bool STRICT>
 __global__ void __launch_bounds__(256)
 k_syn_tail(const T *__restrict__ x, int64_t n, T *__restrict__ dst, int64_t dst_stride, int m, int levels,
-           const __grid_constant__ Taps<T, F> c) {
+           const __grid_constant__ Taps<T, F> c, const __grid_constant__ ThreshEpi epi) {
     using fp = FP<STRICT>;
     using SG = SynTailGeom<T, F>;
     using G = FGeom<F>;
@@ -296,6 +312,15 @@ k_syn_tail(const T *__restrict__ x, int64_t n, T *__restrict__ dst, int64_t dst_
     __syncthreads();
     mbar_wait(&tbar, 0);
     __syncthreads();
+    if (epi.kind >= 0) {   // threshold!(xt, TH, t) as a load epilogue: a_L and every detail band of this column (before the wraps are copied)
+        const double tthr = epi.sigma_dev ? __dmul_rn(*epi.sigma_dev, epi.tfac) : epi.t_host;
+        for (int i = threadIdx.x; i < mL; i += blockDim.x) stage[QAP + i] = thresh_apply<T>(stage[QAP + i], epi.kind, tthr);
+        for (int t = 0; t < levels; ++t) {
+            const int sz = mL << t, off = SG::band_off(mL, t);
+            for (int i = threadIdx.x; i < sz; i += blockDim.x) stage[off + i] = thresh_apply<T>(stage[off + i], epi.kind, tthr);
+        }
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < QAP; i += blockDim.x) { int k = (mL - 1 - i) % mL; if (k < 0) k += mL; stage[QAP - 1 - i] = stage[QAP + k]; }
     for (int t = 0; t < levels; ++t) {
         const int sz = mL << t, off = SG::band_off(mL, t);
@@ -592,7 +617,7 @@ static int32_t run_fused_1d(const PassOp<T> &op, T *y, const T *x, int64_t n, in
             const int64_t dstride = cfg.nstages ? cfg.m : n;
             {
                 LaunchScope scope("fused_syn_tail", st);
-                kern<<<(unsigned)B, 256, smem, st>>>(x, n, dst, dstride, m, cfg.tail_levels, taps);
+                kern<<<(unsigned)B, 256, smem, st>>>(x, n, dst, dstride, m, cfg.tail_levels, taps, op.epi);
             }
             if (!check_launch("fused_syn_tail")) { rc = WB200_ECUDA; return finish(); }
         }
@@ -612,7 +637,7 @@ static int32_t run_fused_1d(const PassOp<T> &op, T *y, const T *x, int64_t n, in
             dim3 grid((unsigned)(ncur / sg.tile), (unsigned)B);
             {
                 LaunchScope scope("fused_syn_tiles", st);
-                kern<<<grid, tile_threads(false), smem, st>>>(asrc, astride, x, n, sg.lv0, dst, dstride, taps, pl);
+                kern<<<grid, tile_threads(false), smem, st>>>(asrc, astride, x, n, sg.lv0, dst, dstride, taps, pl, op.epi, last_overall ? 1 : 0);
             }
             if (!check_launch("fused_syn_tiles")) { rc = WB200_ECUDA; return finish(); }
         }

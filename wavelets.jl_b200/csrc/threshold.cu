@@ -7,43 +7,19 @@
 // Arithmetic follows Julia's promotion rules: t = sigma * dnt.t is Float64, so comparisons and products with t are done in
 // double and rounded to T on the store; medians are exact order statistics (middle(a, b) = a/2 + b/2 in T).
 #include "common.cuh"
+#include "thresh_dev.cuh"
 #include <cmath>
 #include <cstdlib>
 
 namespace wb {
 
 // ---- threshold!(x, TH, t) -------------------------------------------------------------------------------------
-template <typename T> __device__ __forceinline__ double sgn_of(T v) { return (v > 0) ? 1.0 : ((v < 0) ? -1.0 : (double)v); }
-
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_threshold(T *__restrict__ x, int64_t n, int kind, double t_host, const double *__restrict__ sigma_dev, double tfac) {
     const double t = sigma_dev ? __dmul_rn(*sigma_dev, tfac) : t_host;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const T v = x[i];
-        T o = v;
-        switch (kind) {
-        case WB200_TH_HARD: if (fabs((double)v) <= t) o = 0; break;
-        case WB200_TH_SOFT: { const double sh = __dsub_rn(fabs((double)v), t); o = (sh < 0) ? (T)0 : (T)__dmul_rn(sgn_of(v), sh); } break;
-        case WB200_TH_SEMISOFT:
-            if ((double)v <= __dmul_rn(2.0, t)) {          // (sic) x[i], not abs(x[i])
-                const double sh = __dsub_rn(fabs((double)v), t);
-                if (sh < 0) o = 0;
-                else if (__dsub_rn(sh, t) < 0) o = (T)__dmul_rn(__dmul_rn(sgn_of(v), sh), 2.0);
-            }
-            break;
-        case WB200_TH_STEIN: {
-            T vv;
-            if constexpr (sizeof(T) == 4) vv = __fmul_rn(v, v); else vv = __dmul_rn(v, v);
-            const double sh = __dsub_rn(1.0, __ddiv_rn(__dmul_rn(t, t), (double)vv));
-            o = (sh < 0) ? (T)0 : (T)__dmul_rn((double)v, sh);
-        } break;
-        case WB200_TH_NEG: if (v < 0) o = 0; break;
-        case WB200_TH_POS: if (v > 0) o = 0; break;
-        default: break;
-        }
-        x[i] = o;
-    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        x[i] = thresh_apply<T>(x[i], kind, t);
 }
 
 // ---- exact order statistics by radix select (no sort, no host round trip) --------------------------------------
@@ -405,7 +381,18 @@ int32_t denoise_t(T *y, const T *x, int32_t ndim, const int64_t *dims, const WtA
             if (rc == WB200_OK) thr(y);
         } else {
             rc = xform(a0, x, ndim, dims, w, L, 1, dtype, (void *)st, flags);
-            if (rc == WB200_OK) { thr(a0); rc = xform(y, a0, ndim, dims, w, L, 0, dtype, (void *)st, flags); }
+            if (rc == WB200_OK) {
+                // threshold as an epilogue of the inverse transform's loads where the fused 1-D synthesis kernels take the
+                // call (one pass over the coefficients less); otherwise its own elementwise pass
+                int32_t r2 = -1;
+                if (w.wkind == 1 && ndim == 1) {
+                    ThreshEpi e;
+                    e.kind = th_kind; e.t_host = sigma * tfac; e.tfac = tfac; e.sigma_dev = est ? sig : nullptr;
+                    r2 = idwt_filter_thresholded(y, a0, dims[0], 1, w.qmf, w.flen, L, dtype, e, st, flags);
+                }
+                if (r2 == -1) { thr(a0); rc = xform(y, a0, ndim, dims, w, L, 0, dtype, (void *)st, flags); }
+                else rc = r2;
+            }
         }
     } else if (rc == WB200_OK) {
         SpinPlan sp{};
