@@ -774,6 +774,37 @@ def test_lift1d_full_size_strict_vs_oracle(dev):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("wname", ["cdf97", "haar", "db2"])
+def test_lift3d_two_pass_vs_oracle(dev, mode, dtype, wname):
+    """3-D lifting on a cube (transforms_lifting.jl:200-278): register walk along dim 3 + the 2-D lifting level kernel on the
+    planes, generic passes below a 2-D tile; allocating, in-place and batched forms."""
+    from wavelets_b200 import _lib
+    wl = wavelet(getattr(WT, wname), WT.Lifting)
+    for n, L in ((128, 2), (256, 1)):
+        x = rng(n + L + len(wname)).standard_normal((n, n, n)).astype(dtype)
+        _lib.lib().wb200_profile_enable(1)
+        y = wb.dwt(to_gpu(x, dev), wl, L)
+        xr = wb.idwt(y, wl, L)
+        _lib.lib().wb200_profile_enable(0)
+        names = _kernel_names()
+        assert {"walk_lift_fwd", "walk_lift_inv", "fused_lift2d_fwd", "fused_lift2d_inv"} <= names, names
+        ref = orc.dwt_lifting(x, wl.step, wl.norm1, wl.norm2, L)
+        check(y, ref, mode, 3 * L, 8.0)
+        check(xr, orc.dwt_lifting(to_np(y), wl.step, wl.norm1, wl.norm2, L, fw=False), mode, 3 * L, 8.0)
+        if n == 128:                                                     # dwt!(y, scheme, L): in place
+            yi = to_gpu(x, dev).clone(memory_format=torch.preserve_format)
+            yi = wb.colmajor(yi)
+            wb.dwt_(yi, wl, L)
+            check(yi, ref, mode, 3 * L, 8.0)
+            wb.idwt_(yi, wl, L)
+            check(yi, orc.dwt_lifting(ref, wl.step, wl.norm1, wl.norm2, L, fw=False), mode, 3 * L, 8.0)
+    xb = rng(11).standard_normal((128, 128, 128, 2)).astype(dtype)      # two volumes
+    yb = wb.dwtc(to_gpu(xb, dev), wl, 1)
+    check(yb, orc.dwt_lifting_batch(xb, 3, wl.step, wl.norm1, wl.norm2, 1), mode, 3, 8.0)
+    check(wb.idwtc(yb, wl, 1), orc.dwt_lifting_batch(to_np(yb), 3, wl.step, wl.norm1, wl.norm2, 1, fw=False), mode, 3, 8.0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("wname", ["haar", "db2", "db4", "db6", "sym8", "db10"])
 def test_onepass_fir3d_vs_oracle(dev, mode, dtype, wname):
     """One-pass marching 3-D level kernels (fir3d_impl.cuh): one launch per level reads the corner once and writes its

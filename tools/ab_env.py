@@ -22,6 +22,10 @@ elif kind == "wpt":
     wt = wb.wavelet(wb.WT.sym8); x = torch.randn((1024, 1 << 16), device=dev).t()
     Y = wb.wpt(x, wt)
     fwd, inv = (lambda: wb.wpt(x, wt)), (lambda: wb.iwpt(Y, wt))
+elif kind == "lift3d":
+    wt = wb.wavelet(wb.WT.cdf97, wb.WT.Lifting); x = torch.randn((512, 512, 512), device=dev).permute(2, 1, 0)
+    Y = wb.dwt(x, wt, 3)
+    fwd, inv = (lambda: wb.dwt(x, wt, 3)), (lambda: wb.idwt(Y, wt, 3))
 elif kind == "fir3d":
     wt = wb.wavelet(wb.WT.db6); x = torch.randn((512, 512, 512), device=dev).permute(2, 1, 0)
     Y = wb.dwt(x, wt, 3)

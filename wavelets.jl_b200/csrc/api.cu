@@ -615,6 +615,31 @@ static int32_t dispatch_dwt(PassOp<T> &op, void *y, const void *x, const Call &c
             return fir3d_run<T>(op, (T *)y, xin, parked, r1, r1 * r2, r1 * r2 * r3, g, Lf, false, scratch, st);
         }
     }
+    // 3-D lifting on a cube: register walk along dim 3 + the 2-D lifting level kernel on the planes (lift3d.cu), generic
+    // passes for the levels whose corner is smaller than a 2-D tile
+    if (!(flags & WB200_FLAG_FORCE_GENERIC) && g.C == 1 && g.ndim == 3 && lifting &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+        const int Lf = lift3d_levels<T>(op, g, L, fw);
+        if (Lf > 0) {
+            const size_t wbytes = align_up((size_t)g.total() * sizeof(T));
+            const size_t need = wbytes + (L > Lf ? plan_nd_from(c, Lf + 1) : 0);
+            Workspace ws;
+            int32_t rc = ws.init(workspace, ws_bytes, need, st);
+            if (rc != WB200_OK) return rc;
+            T *W = (T *)ws.take(wbytes);
+            if (!W) { set_error("internal: 3-D lifting workspace plan mismatch"); return WB200_EWORKSPACE; }
+            if (fw) {
+                rc = lift3d_run<T>(op, (T *)y, (const T *)x, g, L, Lf, true, W, st);
+                if (rc != WB200_OK || L == Lf) return rc;
+                return run_nd<T>(op, (T *)y, (const T *)y, g, L, true, ws, Lf + 1, L);
+            }
+            if (L > Lf) {
+                rc = run_nd<T>(op, (T *)y, (const T *)x, g, L, false, ws, Lf + 1, L);    // leaves the level-Lf approximation in y's corner
+                if (rc != WB200_OK) return rc;
+            }
+            return lift3d_run<T>(op, (T *)y, (const T *)x, g, L, Lf, false, W, st);
+        }
+    }
     Workspace ws;
     int32_t rc = ws.init(workspace, ws_bytes, plan_dwt(c, L, lifting, inplace, flags | WB200_FLAG_FORCE_GENERIC), st);
     if (rc != WB200_OK) return rc;

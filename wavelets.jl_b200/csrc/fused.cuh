@@ -54,6 +54,15 @@ template <typename T>
 int32_t fir2d_level(const PassOp<T> &op, bool fw, const T *a, int64_t lda, int64_t bsa, const T *xd, int64_t ldx, int64_t bsx,
                     T *o1, int64_t ld1, int64_t bs1, T *o2, int64_t ld2, int64_t bs2, int n, int64_t B, cudaStream_t st);
 
+// ---- 3-D lifting levels in two passes (lift3d.cu): a register walk along dim 3 + the 2-D lifting level kernel on the planes ----
+template <typename T> int lift3d_levels(const PassOp<T> &op, const ArrayGeom &g, int L, bool fw);
+template <typename T>
+int32_t lift3d_run(const PassOp<T> &op, T *y, const T *x, const ArrayGeom &g, int L, int Lf, bool fw, T *W, cudaStream_t st);
+// one 2-D lifting level on B images of n x n with the fused tile kernels (fused2d.cu); pointer contract of fir2d_level
+template <typename T>
+int32_t lift2d_level(const PassOp<T> &op, bool fw, const T *a, int64_t lda, int64_t bsa, const T *xd, int64_t ldx, int64_t bsx,
+                     T *o1, int64_t ld1, int64_t bs1, T *o2, int64_t ld2, int64_t bs2, int n, int64_t B, cudaStream_t st);
+
 // ---- one-pass 3-D filter-bank levels (fir3d_f32.cu / fir3d_f64.cu, fir3d_impl.cuh) ----
 // Number of leading levels the marching kernels take (every dimension of the level's corner whole tiles), their LLL ping-pong
 // scratch, and the level walk (same contract as fused2d_run: forward leaves the level-Lf approximation in y's corner; inverse

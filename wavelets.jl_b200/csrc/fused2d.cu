@@ -790,7 +790,30 @@ int32_t fused2d_run(const PassOp<T> &op, T *y, const T *x, const T *ll_src, int6
 #undef WB_RUN
 }
 
+template <typename T>
+int32_t lift2d_level(const PassOp<T> &op, bool fw, const T *a, int64_t lda, int64_t bsa, const T *xd, int64_t ldx, int64_t bsx,
+                     T *o1, int64_t ld1, int64_t bs1, T *o2, int64_t ld2, int64_t bs2, int n, int64_t B, cudaStream_t st) {
+    LiftCoefs<T> lc;
+    fill_coefs<T>(lc, op.sc);
+    const int id = shape_id<T>(op.sc, fw);
+#define WB_L2(SF, SI_)                                                                                                    \
+    if (fw) return op.strict ? launch_level<T, SF, true, true>(a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, o2, ld2, bs2, n, B, lc, st)    \
+                             : launch_level<T, SF, false, true>(a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, o2, ld2, bs2, n, B, lc, st);  \
+    return op.strict ? launch_level<T, SI_, true, false>(a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, o2, ld2, bs2, n, B, lc, st)         \
+                     : launch_level<T, SI_, false, false>(a, lda, bsa, xd, ldx, bsx, o1, ld1, bs1, o2, ld2, bs2, n, B, lc, st)
+    switch (id) {
+    case 1: WB_L2(ShapeCdf97F, ShapeCdf97I);
+    case 2: WB_L2(ShapeHaarF, ShapeHaarI);
+    case 3: WB_L2(ShapeDb2F, ShapeDb2I);
+    default: break;
+    }
+#undef WB_L2
+    set_error("internal: lift2d_level called for a scheme the fused kernels do not know");
+    return WB200_EARG;
+}
+
 #define WB_INST(T)                                                                                                 \
+    template int32_t lift2d_level<T>(const PassOp<T> &, bool, const T *, int64_t, int64_t, const T *, int64_t, int64_t, T *, int64_t, int64_t, T *, int64_t, int64_t, int, int64_t, cudaStream_t); \
     template int fused2d_levels<T>(const PassOp<T> &, const ArrayGeom &, int, bool);                                \
     template size_t fused2d_scratch_bytes<T>(const ArrayGeom &, int);                                               \
     template int32_t fused2d_run<T>(const PassOp<T> &, T *, const T *, const T *, int64_t, int64_t, const ArrayGeom &, int, bool, void *, cudaStream_t, bool); \
