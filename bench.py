@@ -573,6 +573,9 @@ def run_extras(L, wb, _lib, dev, stream, args, world, rank, barrier, allreduce_m
     w6 = wb.wavelet(wb.WT.db6)
     for L3 in (3, 9):
         res[f"dwt3_db6_512cubed_f32_L{L3}"] = entry(512 ** 3, 4, timed_pair(lambda: wb.dwt(x3, w6, L3), lambda y: wb.idwt(y, w6, L3)), levels=L3)
+    # north_star's lifting leg in 3-D (the reference has no 3-D lifting benchmark of its own): cdf97 lifting on the same cube
+    res["dwt3_cdf97_lifting_512cubed_f32_L3"] = entry(512 ** 3, 4, timed_pair(lambda: wb.dwt(x3, wl, 3), lambda y: wb.idwt(y, wl, 3)), levels=3,
+                                                      note="two passes per level (walk along dim 3 + the 2-D level kernel): compulsory-byte fraction is capped at 0.5")
     del x3
     cleanup()
 
