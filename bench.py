@@ -350,6 +350,25 @@ def copy_probe(dev, stream, world, allreduce_sum, gib=1.0):
     return out
 
 
+def device_copy_probe(x, y, dev, reps=6):
+    """What a plain device copy (torch's `y.copy_(x)`, the kernel MEASURED_PEAKS.json's hbm_gbs was measured with) reaches
+    on the SAME operands right after the timed steps -- same footprint (read 32 GiB, write 32 GiB at 8192 Float32 columns),
+    same board state (power cap, clocks).  Context for `roofline.frac`, whose denominator is the driver's burst figure."""
+    import torch
+    y.copy_(x); y.copy_(x)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(reps):
+        y.copy_(x)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    nbytes = 2 * x.numel() * x.element_size()
+    return {"gbs": nbytes / (ms * 1e-3) / 1e9, "ms": ms, "bytes": nbytes,
+            "note": "torch y.copy_(x) on the step's own operands, back to back after the timed region (sustained, same power state)"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -397,7 +416,14 @@ def main():
     value = N_SIGNAL * B * world / (ms_step_max * 1e-3) / 1e6
     roof = roofline_block(kern, m["ms_total"], args.steps, esz, B, args.dtype, peak, peak_src)
     step_gbs = 4.0 * esz * N_SIGNAL * B / (ms_step * 1e-3) / 1e9
-    x = m.pop("x"); m.pop("y")
+    x = m.pop("x"); ycp = m.pop("y")
+    if roof is not None:
+        try:
+            roof["device_copy_probe"] = device_copy_probe(x, ycp, dev)
+            roof["frac_of_copy_probe"] = roof["achieved"] / roof["device_copy_probe"]["gbs"]
+        except Exception as ex:
+            roof["device_copy_probe"] = {"error": str(ex)[:200]}
+    del ycp
 
     # ---- e2e: host buffers through the C ABI (H2D + D2H inside the timed region) ----
     dims = _lib.dims_array([N_SIGNAL])

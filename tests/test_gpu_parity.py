@@ -582,12 +582,51 @@ def test_fastpass_wpt_full_tree(dev, mode, dtype, n, B, wname):
         _lib.lib().wb200_profile_enable(0)
         names = _kernel_names()
         assert {"wpt_subtree_analysis", "wpt_subtree_synthesis"} <= names, names
-        if n > 4096:
+        if n > 8192:      # two or more full levels above the subtrees: fused K at a time (wptfused.cu)
+            assert {"wpt_fused_levels_analysis", "wpt_fused_levels_synthesis"} <= names, names
+        elif n > 4096:
             assert {"line_filter_analysis", "line_filter_synthesis"} <= names, names
         yn, xn = to_np(y), to_np(xr)
         for b in range(B):
             check(np.ascontiguousarray(yn[:, b]), orc.wpt_filter(x[:, b].copy(), wf.qmf, t), mode, L, 4.0)
             check(np.ascontiguousarray(xn[:, b]), orc.wpt_filter(yn[:, b].copy(), wf.qmf, t, fw=False), mode, L, 4.0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n,B,wname", [(65536, 2, "sym8"), (32768, 3, "db4"), (3 * 16384, 2, "haar"), (16384, 2, "db2"),
+                                        (65536, 1, "db10"), (65536, 2, "db6"), (131072, 1, "sym8"), (5 * 8192, 1, "db9")])
+def test_wpt_fused_levels(dev, mode, dtype, n, B, wname):
+    """runs of full packet levels above the on-chip subtrees go K at a time through k_pkt_ana / k_pkt_syn (wptfused.cu):
+    K = 4 (haar, sym8, db9), 3 (db4) or 2 (db2, db6, db10) by the filter's detail shift; full trees, a tree whose top three
+    levels are full with a dwt-like remainder, and the in-place forms"""
+    from wavelets_b200 import _lib
+    wf = wavelet(wavelet_class(wname))
+    x = rng(n + B).standard_normal((n, B)).astype(dtype)
+    Lmax = wb.maxtransformlevels(n)
+    top3 = wb.maketree(n, 3, "full")
+    for lv in range(3, Lmax):                                  # below level 3: only the leftmost node keeps splitting
+        top3[2 ** lv - 1] = 1
+    assert wb.isvalidtree(n, top3)
+    for t in (wb.maketree(n, Lmax, "full"), top3):
+        _lib.lib().wb200_profile_enable(1)
+        y = wb.wpt(to_gpu(x, dev), wf, t)
+        xr = wb.iwpt(y, wf, t)
+        _lib.lib().wb200_profile_enable(0)
+        names = _kernel_names()
+        assert {"wpt_fused_levels_analysis", "wpt_fused_levels_synthesis"} <= names, names
+        yn, xn = to_np(y), to_np(xr)
+        for b in range(B):
+            check(np.ascontiguousarray(yn[:, b]), orc.wpt_filter(x[:, b].copy(), wf.qmf, t), mode, Lmax, 4.0)
+            check(np.ascontiguousarray(xn[:, b]), orc.wpt_filter(yn[:, b].copy(), wf.qmf, t, fw=False), mode, Lmax, 4.0)
+    # wpt!(y, x, filter, tree): the out-of-place form lands in the caller's array whatever the number of sweeps
+    t = wb.maketree(n, Lmax, "full")
+    xg = to_gpu(x, dev)
+    y = wb.wpt(xg, wf, t)
+    z = torch.empty_like(y)
+    wb.wpt_(z, xg, wf, t)
+    assert torch.equal(z, y)
+    wb.iwpt_(z, y, wf, t)
+    assert torch.equal(z, wb.iwpt(y, wf, t))
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -412,7 +412,23 @@ static int32_t run_wpt(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t
     }
     struct Sweep { int lv, count; };
     std::vector<Sweep> sweeps;
-    for (int lv = 0; lv < lv_sub; ++lv) sweeps.push_back({lv, 1});
+    // levels above the subtree run: runs of FULL levels are fused K at a time (wptfused.cu, filter path), the rest go one
+    // sweep per level
+    const bool fuse_ok = !op.lifting && !op.generic_only && C == 1 && ((n * (int64_t)sizeof(T)) % 16) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
+    const int kfuse = fuse_ok ? wpt_fused_max_levels(op.fc.F) : 0;
+    auto level_full = [&](int lv) {
+        const int64_t nodes = (int64_t)1 << lv;
+        for (int64_t k = 0; k < nodes; ++k) if (!tree[(nodes - 1) + k]) return false;
+        return true;
+    };
+    for (int lv = 0; lv < lv_sub;) {
+        int run = 0;
+        if (kfuse >= 2) while (lv + run < lv_sub && run < kfuse && level_full(lv + run)) ++run;
+        while (run >= 2 && !wpt_fused_ok((int)sizeof(T), op.fc.F, n >> lv, run)) --run;   // the kernels' own acceptance test
+        if (run >= 2) { sweeps.push_back({lv, run}); lv += run; }
+        else { sweeps.push_back({lv, 1}); ++lv; }
+    }
     if (lv_sub < deep) sweeps.push_back({lv_sub, deep - lv_sub});
     if (!fw) std::reverse(sweeps.begin(), sweeps.end());
     // sweep i writes D_i; the last sweep must land in y unless that would make sweep 0 in place (x == y)
@@ -426,11 +442,18 @@ static int32_t run_wpt(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t
         const int64_t nj = n >> lv, nodes = (int64_t)1 << lv;
         const T *S = (i == 0) ? x : dst2(i - 1);
         T *D = dst2(i);
-        if (sweeps[i].count > 1) {
+        if (sweeps[i].count > 1 && lv >= lv_sub) {
             const int r = fast_wpt_subtree<T>(S, D, n, nj, sweeps[i].count, nodes, B, op.fc, op.strict, fw, op.st);
             if (r < 0) return WB200_ECUDA;
             if (r > 0) continue;
             set_error("internal: packet subtree kernel rejected a planned sweep");
+            return WB200_ECUDA;
+        }
+        if (sweeps[i].count > 1) {
+            const int r = fast_wpt_fused_levels<T>(S, D, n, nj, sweeps[i].count, nodes, B, op.fc, op.strict, fw, op.st);
+            if (r < 0) return WB200_ECUDA;
+            if (r > 0) continue;
+            set_error("internal: fused packet-level kernel rejected a planned sweep");
             return WB200_ECUDA;
         }
         Extent e; e.len = nj; e.n[0] = C; e.n[1] = nodes; e.n[2] = 1; e.n[3] = B;

@@ -153,6 +153,13 @@ int fast_wpt_subtree(const T *S, T *D, int64_t n, int64_t m, int levels, int64_t
 
 int wpt_subtree_max_samples(int esize);   // largest packet node the on-chip subtree kernels take (fastpass.cu)
 
+// K consecutive full packet levels of large nodes in one launch (wptfused.cu): `nodes` nodes of nj samples per signal
+template <typename T>
+int fast_wpt_fused_levels(const T *S, T *D, int64_t n, int64_t nj, int K, int64_t nodes, int64_t B,
+                          const FilterCoefs<T> &fc, bool strict, bool fw, cudaStream_t st);
+int wpt_fused_max_levels(int F);          // most levels one such launch fuses for an F-tap filter (0: not covered)
+bool wpt_fused_ok(int esize, int F, int64_t nj, int K);   // the kernels' own acceptance test, for planning
+
 template <typename T> struct PassOp {
     ThreshEpi epi;
     bool lifting;

@@ -65,16 +65,11 @@ k_line_ana(View<const T> src, View<T> dlo, View<T> dhi, Extent e, int tile, int 
     T *dbase = hi + sl + G::DS;
     const int64_t room = nh - sl - G::DS;
     const int wrap_at = room < (int64_t)ND ? (int)room : 0x7fffffff;
-    const int wrap_by = (int)nh;
-    auto store_d = [&](int p, const T (&d)[PA]) {
-        T *q = dbase + (p >= wrap_at ? p - wrap_by : p);
-        if constexpr (PA == 2) gstore2(q, d[0], d[1]); else __stcs(q, d[0]);
-    };
     T *abase = lo + sl;
     auto store_a = [&](int p, const T (&a)[PA]) {
         if constexpr (PA == 2) gstore2(abase + p, a[0], a[1]); else __stcs(abase + p, a[0]);
     };
-    ana_level<T, F, STRICT>(buf, ND, ND, c, store_a, store_d);
+    ana_level<T, F, STRICT>(buf, ND, ND, c, store_a, dbase, dbase - nh, wrap_at);
 }
 
 template <typename T, int F, bool STRICT>
@@ -228,13 +223,14 @@ k_walk_syn(View<const T> slo, View<const T> shi, View<const T> salt, int64_t thr
 // write of the node.  Sub-node j of level l occupies [j*ml, (j+1)*ml) of the node's span and is replaced in place by
 // [approximation | detail] (natural / Paley order, transforms_filter.jl:337-353).
 // ===================================================================================================
+static int env_int_fp(const char *name, int dflt) { const char *v = std::getenv(name); return (v && *v) ? std::atoi(v) : dflt; }
 constexpr int WPT_SUB_MAX = 4096;        // default.  r02 sweep (sym8, 2^16, 1024 signals, wpt + iwpt): 4096 -> 2.40 ms, 8192 -> 2.35 ms
                                          // (one HBM sweep less, three resident CTAs instead of seven), 16384 -> 3.70 ms (one CTA per SM)
 int wpt_subtree_max_samples(int esize) {
-    (void)esize;
     const char *e = std::getenv("WB200_WPT_SUBMAX");
     int v = (e && *e) ? std::atoi(e) : WPT_SUB_MAX;
-    if (v > 8192) v = 8192;
+    const int cap = esize == 4 ? 16384 : 8192;        // two ping-pong buffers of m samples: 128 KB of shared memory at most
+    if (v > cap) v = cap;
     int p = 2;
     while (p * 2 <= v) p *= 2;               // a power of two
     return p;
@@ -314,6 +310,127 @@ __device__ __forceinline__ void tiny_syn(const T (&a)[NH], const T (&d)[NH], T (
     }
 }
 
+// One analysis level of the sub-nodes of nh-sample components (nh a multiple of 4) held split in shared memory: a thread
+// takes one 16-byte chunk of output pairs of one sub-node.  The detail pairs it produces are the ones DS = 4 CL further on
+// (d[k + DS] reads x[2k + 2 DS + 2 - F ...]: with DS >= Q - 1 that is the same register window as a[k], cf. FGeom), so a
+// thread loads CL + 1 chunks per component instead of 2 CL + 1 (sym8: 6 LDS.128 per 128 FMA instead of 10) and stores its
+// detail chunk CL chunks further round the node.  P2 (the chunk count per component is a power of two -- every level of a
+// dyadic signal): node / chunk indices and the periodic wrap are shifts and masks; otherwise divisions and
+// compare-and-reset (the division form cost ~110 of the 260 instructions of an iteration).
+template <typename T, int F, bool STRICT, bool P2>
+__device__ __forceinline__ void wpt_sub_ana_chunks(const T *__restrict__ in, T *__restrict__ out, int m, int nh, bool last,
+                                                   const Taps<T, F> &c) {
+    using fp = FP<STRICT>;
+    constexpr int Q = F / 2;
+    constexpr int CL = (Q - 1 + 3) / 4;          // chunks of reach; DS = 4 CL
+    constexpr int NCH = CL + 1;
+    constexpr int DO = 4 * CL + 1 - Q;           // window offset of the detail taps (>= 0)
+    const int mh = m >> 1, hh = nh >> 1, ml = nh << 1;
+    const int cpn = nh >> 2;
+    const int sh = P2 ? (31 - __clz(cpn)) : 0, mask = cpn - 1;
+    for (int idx = threadIdx.x; idx < (m >> 3); idx += blockDim.x) {
+        int j, c0;
+        if constexpr (P2) { j = idx >> sh; c0 = idx & mask; } else { j = idx / cpn; c0 = idx - j * cpn; }
+        const T *E = in + j * nh, *O = E + mh;
+        T we[4 * NCH], wo[4 * NCH];
+        int ci = c0;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            const int cc = P2 ? ((c0 + i) & mask) : ci;
+            T t4[4];
+            ld4(t4, E + 4 * cc);
+            we[4 * i] = t4[0]; we[4 * i + 1] = t4[1]; we[4 * i + 2] = t4[2]; we[4 * i + 3] = t4[3];
+            ld4(t4, O + 4 * cc);
+            wo[4 * i] = t4[0]; wo[4 * i + 1] = t4[1]; wo[4 * i + 2] = t4[2]; wo[4 * i + 3] = t4[3];
+            if constexpr (!P2) { if (++ci == cpn) ci = 0; }
+        }
+        T av[4], dv[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            // a[k0 + r] = sum_t h[t] x[2 (k0 + r) + t]
+            T acc = fp::mul(c.h[0], we[r]);
+#pragma unroll
+            for (int t = 1; t < F; ++t) acc = fp::mac(acc, c.h[t], (t & 1) ? wo[r + (t - 1) / 2] : we[r + t / 2]);
+            av[r] = acc;
+            // d[k0 + 4 CL + r] = sum_t g[F-1-t] x[2 (k0 + 4 CL + r) + 2 - F + t]
+            T qd = fp::mul(c.g[F - 1], we[DO + r]);
+#pragma unroll
+            for (int t = 1; t < F; ++t) qd = fp::mac(qd, c.g[F - 1 - t], (t & 1) ? wo[DO + r + (t - 1) / 2] : we[DO + r + t / 2]);
+            dv[r] = qd;
+        }
+        int cd;                                   // chunk the detail pairs belong to
+        if constexpr (P2) cd = (c0 + CL) & mask; else cd = (c0 + CL) % cpn;
+        const int k0 = 4 * c0, kd = 4 * cd;
+        if (!last) {
+            T *ea = out + (2 * j) * hh + (k0 >> 1), *ed = out + (2 * j + 1) * hh + (kd >> 1);
+            st2(ea, av[0], av[2]); st2(ea + mh, av[1], av[3]);
+            st2(ed, dv[0], dv[2]); st2(ed + mh, dv[1], dv[3]);
+        } else {
+            st4(out + j * ml + k0, av[0], av[1], av[2], av[3]);
+            st4(out + j * ml + nh + kd, dv[0], dv[1], dv[2], dv[3]);
+        }
+    }
+}
+
+// One synthesis level of band-split sub-nodes (a_j at [j nh), d_j at m/2 + [j nh)); see wpt_sub_ana_chunks for P2.
+template <typename T, int F, bool STRICT, bool P2>
+__device__ __forceinline__ void wpt_sub_syn_chunks(const T *__restrict__ in, T *__restrict__ out, int m, int nh, const Taps<T, F> &c) {
+    using fp = FP<STRICT>;
+    constexpr int Q = F / 2;
+    constexpr int CL = (Q - 1 + 3) / 4;
+    const int mh = m >> 1, ml = nh << 1;
+    const int cpn = nh >> 2;
+    const int sh = P2 ? (31 - __clz(cpn)) : 0, mask = cpn - 1;
+    for (int idx = threadIdx.x; idx < (m >> 3); idx += blockDim.x) {
+        int j, c0;
+        if constexpr (P2) { j = idx >> sh; c0 = idx & mask; } else { j = idx / cpn; c0 = idx - j * cpn; }
+        const T *A = in + j * nh, *Dd = A + mh;
+        T wa[4 * (CL + 1)], wd[4 * (CL + 1)];
+        int ci = c0 - CL;
+        if constexpr (!P2) { ci %= cpn; if (ci < 0) ci += cpn; }
+#pragma unroll
+        for (int i = 0; i <= CL; ++i) {
+            const int cc = P2 ? ((ci + i) & mask) : ci;
+            T t4[4];
+            ld4(t4, A + 4 * cc);
+            wa[4 * i] = t4[0]; wa[4 * i + 1] = t4[1]; wa[4 * i + 2] = t4[2]; wa[4 * i + 3] = t4[3];
+            if constexpr (!P2) { if (++ci == cpn) ci = 0; }
+        }
+        ci = c0;
+#pragma unroll
+        for (int i = 0; i <= CL; ++i) {
+            const int cc = P2 ? ((ci + i) & mask) : ci;
+            T t4[4];
+            ld4(t4, Dd + 4 * cc);
+            wd[4 * i] = t4[0]; wd[4 * i + 1] = t4[1]; wd[4 * i + 2] = t4[2]; wd[4 * i + 3] = t4[3];
+            if constexpr (!P2) { if (++ci == cpn) ci = 0; }
+        }
+        T xo[8];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            T rae = fp::mul(c.h[2 * (Q - 1)], wa[4 * CL + r - (Q - 1)]);
+            T rao = fp::mul(c.h[2 * (Q - 1) + 1], wa[4 * CL + r - (Q - 1)]);
+#pragma unroll
+            for (int t = Q - 2; t >= 0; --t) {
+                rae = fp::mac(rae, c.h[2 * t], wa[4 * CL + r - t]);
+                rao = fp::mac(rao, c.h[2 * t + 1], wa[4 * CL + r - t]);
+            }
+            T rde = fp::mul(c.g[1], wd[r]);
+            T rdo = fp::mul(c.g[0], wd[r]);
+#pragma unroll
+            for (int t = 1; t < Q; ++t) {
+                rde = fp::mac(rde, c.g[2 * t + 1], wd[r + t]);
+                rdo = fp::mac(rdo, c.g[2 * t], wd[r + t]);
+            }
+            xo[2 * r] = fp::add(rae, rde);
+            xo[2 * r + 1] = fp::add(rao, rdo);
+        }
+        T *o = out + (j & 1) * mh + (j >> 1) * ml + 8 * c0;
+        st4(o, xo[0], xo[1], xo[2], xo[3]);
+        st4(o + 4, xo[4], xo[5], xo[6], xo[7]);
+    }
+}
+
 // Shared-memory layouts (both kernels ping-pong between two m-sample buffers):
 //   analysis input of a level  : every sub-node SPLIT into its polyphase components, all even parts first --
 //        node j (length ml, nh = ml/2): E_j at [j nh, (j+1) nh), O_j at m/2 + [j nh, (j+1) nh).  A warp's 16-byte loads are
@@ -322,7 +439,7 @@ __device__ __forceinline__ void tiny_syn(const T (&a)[NH], const T (&d)[NH], T (
 //   synthesis input of a level : all approximation bands first -- a_j at [j nh, ..), d_j at m/2 + [j nh, ..);
 //   the last analysis level writes, and the first synthesis level reads, the natural packet order [a_j | d_j] per node.
 template <typename T, int F, bool STRICT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int levels, int64_t nodes,
               const __grid_constant__ Taps<T, F> c) {
     using fp = FP<STRICT>;
@@ -347,43 +464,8 @@ k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
         // child cidx (2j: approximation, 2j+1: detail) of the next level: E' at cidx*hh, O' at mh + cidx*hh
         if (nh >= 4 && (nh & 3) == 0) {
             const int cpn = nh >> 2;                          // 16-byte chunks per component of a sub-node
-            for (int idx = threadIdx.x; idx < (m >> 3); idx += blockDim.x) {
-                const int j = idx / cpn, c0 = idx - j * cpn;
-                const T *E = in + j * nh, *O = E + mh;
-                T we[4 * NCH], wo[4 * NCH];
-                int ci = c0 - CL;
-                ci %= cpn; if (ci < 0) ci += cpn;
-#pragma unroll
-                for (int i = 0; i < NCH; ++i) {
-                    T t4[4];
-                    ld4(t4, E + 4 * ci);
-                    we[4 * i] = t4[0]; we[4 * i + 1] = t4[1]; we[4 * i + 2] = t4[2]; we[4 * i + 3] = t4[3];
-                    ld4(t4, O + 4 * ci);
-                    wo[4 * i] = t4[0]; wo[4 * i + 1] = t4[1]; wo[4 * i + 2] = t4[2]; wo[4 * i + 3] = t4[3];
-                    if (++ci == cpn) ci = 0;
-                }
-                T av[4], dv[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    T acc = fp::mul(c.h[0], we[4 * CL + r]);
-#pragma unroll
-                    for (int t = 1; t < F; ++t) acc = fp::mac(acc, c.h[t], (t & 1) ? wo[4 * CL + r + (t - 1) / 2] : we[4 * CL + r + t / 2]);
-                    av[r] = acc;
-                    T qd = fp::mul(c.g[F - 1], we[4 * CL + r + 1 - Q]);
-#pragma unroll
-                    for (int t = 1; t < F; ++t) qd = fp::mac(qd, c.g[F - 1 - t], (t & 1) ? wo[4 * CL + r + 1 - Q + (t - 1) / 2] : we[4 * CL + r + 1 - Q + t / 2]);
-                    dv[r] = qd;
-                }
-                const int k0 = 4 * c0;
-                if (!last) {
-                    T *ea = out + (2 * j) * hh + (k0 >> 1), *ed = out + (2 * j + 1) * hh + (k0 >> 1);
-                    st2(ea, av[0], av[2]); st2(ea + mh, av[1], av[3]);
-                    st2(ed, dv[0], dv[2]); st2(ed + mh, dv[1], dv[3]);
-                } else {
-                    st4(out + j * ml + k0, av[0], av[1], av[2], av[3]);
-                    st4(out + j * ml + nh + k0, dv[0], dv[1], dv[2], dv[3]);
-                }
-            }
+            if ((cpn & (cpn - 1)) == 0) wpt_sub_ana_chunks<T, F, STRICT, true>(in, out, m, nh, last, c);
+            else wpt_sub_ana_chunks<T, F, STRICT, false>(in, out, m, nh, last, c);
         } else if (ml == 4) {
             for (int j = threadIdx.x; j < (m >> 2); j += blockDim.x) {
                 const T xe[2] = {in[2 * j], in[2 * j + 1]}, xo[2] = {in[mh + 2 * j], in[mh + 2 * j + 1]};
@@ -435,7 +517,7 @@ k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
 }
 
 template <typename T, int F, bool STRICT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int levels, int64_t nodes,
               const __grid_constant__ Taps<T, F> c) {
     using fp = FP<STRICT>;
@@ -460,51 +542,8 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
         // node j's output (ml samples) is band (j & 1) of its parent j >> 1 for the next, shallower level
         if (nh >= 4 && (nh & 3) == 0) {
             const int cpn = nh >> 2;
-            for (int idx = threadIdx.x; idx < (m >> 3); idx += blockDim.x) {
-                const int j = idx / cpn, c0 = idx - j * cpn;
-                const T *A = in + j * nh, *Dd = A + mh;
-                T wa[4 * (CL + 1)], wd[4 * (CL + 1)];
-                int ci = c0 - CL;
-                ci %= cpn; if (ci < 0) ci += cpn;
-#pragma unroll
-                for (int i = 0; i <= CL; ++i) {
-                    T t4[4];
-                    ld4(t4, A + 4 * ci);
-                    wa[4 * i] = t4[0]; wa[4 * i + 1] = t4[1]; wa[4 * i + 2] = t4[2]; wa[4 * i + 3] = t4[3];
-                    if (++ci == cpn) ci = 0;
-                }
-                ci = c0;
-#pragma unroll
-                for (int i = 0; i <= CL; ++i) {
-                    T t4[4];
-                    ld4(t4, Dd + 4 * ci);
-                    wd[4 * i] = t4[0]; wd[4 * i + 1] = t4[1]; wd[4 * i + 2] = t4[2]; wd[4 * i + 3] = t4[3];
-                    if (++ci == cpn) ci = 0;
-                }
-                T xo[8];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    T rae = fp::mul(c.h[2 * (Q - 1)], wa[4 * CL + r - (Q - 1)]);
-                    T rao = fp::mul(c.h[2 * (Q - 1) + 1], wa[4 * CL + r - (Q - 1)]);
-#pragma unroll
-                    for (int t = Q - 2; t >= 0; --t) {
-                        rae = fp::mac(rae, c.h[2 * t], wa[4 * CL + r - t]);
-                        rao = fp::mac(rao, c.h[2 * t + 1], wa[4 * CL + r - t]);
-                    }
-                    T rde = fp::mul(c.g[1], wd[r]);
-                    T rdo = fp::mul(c.g[0], wd[r]);
-#pragma unroll
-                    for (int t = 1; t < Q; ++t) {
-                        rde = fp::mac(rde, c.g[2 * t + 1], wd[r + t]);
-                        rdo = fp::mac(rdo, c.g[2 * t], wd[r + t]);
-                    }
-                    xo[2 * r] = fp::add(rae, rde);
-                    xo[2 * r + 1] = fp::add(rao, rdo);
-                }
-                T *o = out + (j & 1) * mh + (j >> 1) * ml + 8 * c0;
-                st4(o, xo[0], xo[1], xo[2], xo[3]);
-                st4(o + 4, xo[4], xo[5], xo[6], xo[7]);
-            }
+            if ((cpn & (cpn - 1)) == 0) wpt_sub_syn_chunks<T, F, STRICT, true>(in, out, m, nh, c);
+            else wpt_sub_syn_chunks<T, F, STRICT, false>(in, out, m, nh, c);
         } else if (ml == 4) {
             for (int j = threadIdx.x; j < (m >> 2); j += blockDim.x) {
                 const T a[2] = {in[2 * j], in[2 * j + 1]}, d[2] = {in[mh + 2 * j], in[mh + 2 * j + 1]};
@@ -561,16 +600,20 @@ static int wpt_sub_F(const T *S, T *D, int64_t n, int m, int levels, int64_t nod
     const int64_t nblk = nodes * B;
     if (nblk > 0x7fffffffLL) return 0;
     const size_t smem = (size_t)2 * m * sizeof(T);
+    // two thread-iterations per level: a node of 4096 samples runs 256 threads (six CTAs per SM), 8192 -> 512, 16384 -> 1024
+    int nthr = env_int_fp("WB200_WPT_SUB_NT", 0);
+    if (nthr < 32 || nthr > 1024) nthr = m >= 16384 ? 1024 : (m >= 8192 ? 512 : 256);
+    nthr &= ~31;
     if (fw) {
         auto kern = k_wpt_sub_ana<T, F, STRICT>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
         LaunchScope scope("wpt_subtree_analysis", st);
-        kern<<<(unsigned)nblk, 256, smem, st>>>(S, D, n, m, levels, nodes, taps);
+        kern<<<(unsigned)nblk, nthr, smem, st>>>(S, D, n, m, levels, nodes, taps);
     } else {
         auto kern = k_wpt_sub_syn<T, F, STRICT>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
         LaunchScope scope("wpt_subtree_synthesis", st);
-        kern<<<(unsigned)nblk, 256, smem, st>>>(S, D, n, m, levels, nodes, taps);
+        kern<<<(unsigned)nblk, nthr, smem, st>>>(S, D, n, m, levels, nodes, taps);
     }
     return check_launch("wpt_subtree") ? 1 : -1;
 }
@@ -669,14 +712,12 @@ static int fast_syn_F(const View<const T> &slo, const View<const T> &shi, const 
         if (tile < 64 || (e.len * (int64_t)sizeof(T)) % 32 != 0 || e.len > ((int64_t)1 << 30)) return 0;
         if (!aligned16_view(slo, e) || !aligned16_view(shi, e) || (has_alt && !aligned16_view(salt, e)) ||
             !aligned16_view(View<const T>{dst.p, dst.ls, {dst.s[0], dst.s[1], dst.s[2], dst.s[3]}}, e)) return 0;
-        auto dn4 = [](int v) { return (v >= 0) ? (v & ~3) : -(((-v) + 3) & ~3); };
-        auto up4 = [](int v) { return (v + 3) & ~3; };
-        SynPlan pl;
+        SynPlan pl;      // ranges cut for the four-pair form of syn_level (fused1d_dev.cuh)
         memset(&pl, 0, sizeof(pl));
         pl.K = 1; pl.tile = tile;
         pl.rlo[0] = 0; pl.rhi[0] = tile;
-        pl.rlo[1] = dn4(-G::QA); pl.rhi[1] = tile / 2;
-        pl.dlo[1] = 0; pl.dhi[1] = up4(tile / 2 + G::QD - 2);
+        pl.rlo[1] = -G::Q4; pl.rhi[1] = tile / 2;
+        pl.dlo[1] = 0; pl.dhi[1] = tile / 2 + G::Q4;
         pl.doff[1] = 0;
         pl.aoff = pl.dhi[1] - pl.dlo[1];
         const int64_t nh = e.len / 2;

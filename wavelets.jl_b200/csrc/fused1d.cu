@@ -62,20 +62,15 @@ k_ana_tiles(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, in
         const int64_t nl = ncur >> l;              // length of the d band of this level (and of its approximation)
         const int64_t sl = s >> l;
         // d_j lives at y[n0/2^j .. n0/2^(j-1)); this tile's details start DS further (same register window as the
-        // approximation) and wrap to the band start in the line's last tile: 32-bit tile-relative addressing
+        // approximation) and wrap to the band start in the line's last tile
         T *dbase = yc + (n0 >> (lvl0 + l)) + sl + G::DS;
         const int64_t room = nl - sl - G::DS;                      // pairs before the wrap
         const int wrap_at = room < (int64_t)pl.ND[l] ? (int)room : 0x7fffffff;
-        const int wrap_by = (int)(nl < 0x7fffffff ? nl : 0);
-        auto store_d = [&](int p, const T (&d)[PA]) {
-            T *q = dbase + (p >= wrap_at ? p - wrap_by : p);
-            if constexpr (PA == 2) gstore2(q, d[0], d[1]); else __stcs(q, d[0]);
-        };
         if (l < pl.K) {
             auto store_a = [&](int p, const T (&a)[PA]) {
                 if constexpr (PA == 2) store2(out + p, a[0], a[1]); else out[p] = a[0];
             };
-            ana_level<T, F, STRICT>(in, pl.NA[l], pl.ND[l], c, store_a, store_d);
+            ana_level<T, F, STRICT>(in, pl.NA[l], pl.ND[l], c, store_a, dbase, dbase - nl, wrap_at);
             __syncthreads();
             const T *t = in; in = out; out = const_cast<T *>(t);
         } else {
@@ -83,7 +78,7 @@ k_ana_tiles(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, in
             auto store_a = [&](int p, const T (&a)[PA]) {
                 if constexpr (PA == 2) gstore2(dst + p, a[0], a[1]); else __stcs(dst + p, a[0]);
             };
-            ana_level<T, F, STRICT>(in, pl.NA[l], pl.ND[l], c, store_a, store_d);
+            ana_level<T, F, STRICT>(in, pl.NA[l], pl.ND[l], c, store_a, dbase, dbase - nl, wrap_at);
         }
     }
 }
@@ -136,21 +131,19 @@ k_ana_tail(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, int
         T *dband = yc + (n >> lvl);
         const bool last = (l == levels);
         if (ml >= 64 && (nh % PA) == 0) {
-            auto store_d = [&](int p, const T (&d)[PA]) {
-                int idx = p + G::DS;
-                if (idx >= nh) idx -= nh;
-                if constexpr (PA == 2) gstore2(dband + idx, d[0], d[1]); else __stcs(dband + idx, d[0]);
-            };
+            // d[p + DS] wraps to the band start at pair nh - DS
+            T *d0 = dband + G::DS, *d1 = dband + G::DS - nh;
+            const int wrap_at = nh - G::DS;
             if (last) {
                 auto store_a = [&](int p, const T (&a)[PA]) {
                     if constexpr (PA == 2) gstore2(yc + p, a[0], a[1]); else __stcs(yc + p, a[0]);
                 };
-                ana_level<T, F, STRICT>(in, nh, nh, c, store_a, store_d);
+                ana_level<T, F, STRICT>(in, nh, nh, c, store_a, d0, d1, wrap_at);
             } else {
                 auto store_a = [&](int p, const T (&a)[PA]) {
                     if constexpr (PA == 2) store2(out + p, a[0], a[1]); else out[p] = a[0];
                 };
-                ana_level<T, F, STRICT>(in, nh, nh, c, store_a, store_d);
+                ana_level<T, F, STRICT>(in, nh, nh, c, store_a, d0, d1, wrap_at);
                 __syncthreads();
                 for (int i = threadIdx.x; i < TG::HW; i += blockDim.x) out[nh + i] = out[i % nh];   // periodic wrap
             }
@@ -484,16 +477,18 @@ template <typename T> static size_t ana_smem(const AnaPlan &pl) {
 
 template <int F> static bool make_syn_plan(SynPlan &pl, const Stage &sg, int64_t ncur, size_t &smem_elems) {
     using G = FGeom<F>;
-    auto dn4 = [](int v) { return (v >= 0) ? (v & ~3) : -(((-v) + 3) & ~3); };
-    auto up4 = [](int v) { return (v + 3) & ~3; };
+    // staged ranges are cut for the four-pair form of syn_level (16-byte windows): every range starts on a multiple of 8
+    // samples of its level (so the half-rate index of the level above is a multiple of 4), with Q4 samples of a_l in front of
+    // the first output pair and Q4 samples of d_l behind the last one; the two-pair form (Float64) needs no more than that
+    auto dn8 = [](int v) { return (v >= 0) ? (v & ~7) : -(((-v) + 7) & ~7); };
     pl.K = sg.K; pl.tile = sg.tile;
     pl.rlo[0] = 0; pl.rhi[0] = sg.tile;
     pl.dlo[0] = pl.dhi[0] = pl.doff[0] = 0;
     for (int l = 1; l <= sg.K; ++l) {
-        pl.rlo[l] = dn4(pl.rlo[l - 1] / 2 - G::QA);   // rlo[l-1] is a multiple of 4, so /2 is exact
+        pl.rlo[l] = dn8(pl.rlo[l - 1] / 2 - G::Q4);   // rlo[l-1] is a multiple of 8, so /2 is a multiple of 4
         pl.rhi[l] = pl.rhi[l - 1] / 2;
-        pl.dlo[l] = dn4(pl.rlo[l - 1] / 2);
-        pl.dhi[l] = up4(pl.rhi[l - 1] / 2 + G::QD - 2);
+        pl.dlo[l] = pl.rlo[l - 1] / 2;
+        pl.dhi[l] = pl.rhi[l - 1] / 2 + G::Q4;
     }
     size_t off = 0;
     for (int l = 1; l <= sg.K; ++l) { pl.doff[l] = (int)off; off += (size_t)(pl.dhi[l] - pl.dlo[l]); }

@@ -128,6 +128,8 @@ template <int F, int PA = 2> struct FGeom {
     // synthesis: two output pairs (u, u+1) read a[u-QA .. u+2) and d[u .. u+QD)
     static constexpr int QA = ((Q - 1) + 1) & ~1;
     static constexpr int QD = ((Q + 1) + 1) & ~1;
+    // 4-byte samples: FOUR output pairs (u .. u+3) from 16-byte windows a[u-Q4 .. u+4) and d[u .. u+4+Q4)
+    static constexpr int Q4 = ((Q - 1) + 3) & ~3;
 };
 
 template <typename T, int F> struct Taps {
@@ -151,12 +153,45 @@ struct AnaPlan {
 // one analysis level out of shared memory: `in` holds NAprev valid samples of a_{l-1}
 //   a[j]      = sum_m h[m]     in[2j + m]                 (increasing m)
 //   d[j + DS] = sum_p g[F-1-p] in[2j + WO + p]            (increasing input index)
-template <typename T, int F, bool STRICT, typename SA, typename SD>
-__device__ __forceinline__ void ana_level(const T *__restrict__ in, int NA, int ND, const Taps<T, F> &c, SA store_a, SD store_d) {
+// Approximations are produced for p < NA (halo included) and handed to store_a; details for p < ND go to d0 + p, or to
+// d1 + p from pair `wrap_at` on (the band's periodic wrap inside the last tile of a line; wrap_at >= ND: no wrap).
+// Three branch-free loops over one running index (details before the wrap, after it, approximation-only halo) keep the
+// inner loop at loads + FMAs + two stores: the former single loop carried a predicated detail block and re-derived the wrap
+// address per iteration (27 of its 59 instructions per iteration were neither loads, stores nor arithmetic).
+template <typename T, int F, bool STRICT, typename SA>
+__device__ __forceinline__ void ana_level(const T *__restrict__ in, int NA, int ND, const Taps<T, F> &c, SA store_a,
+                                          T *__restrict__ d0, T *__restrict__ d1, int wrap_at) {
     using fp = FP<STRICT>;
     constexpr int PA = AnaPairs<T>::value;
     using G = FGeom<F, PA>;
-    for (int p = PA * threadIdx.x; p < NA; p += PA * blockDim.x) {
+    const int step = PA * blockDim.x;
+    int p = PA * threadIdx.x;
+    const int e1 = wrap_at < ND ? wrap_at : ND;
+#pragma unroll 1
+    for (int seg = 0; seg < 2; ++seg) {
+        T *__restrict__ dp = (seg ? d1 : d0) + p;      // running detail pointer: one 64-bit add per iteration
+        const int e = seg ? ND : e1;
+        for (; p < e; p += step, dp += step) {
+            T w[G::WIN];
+            load_window<G::WIN>(w, in + 2 * p);
+            T a[PA], d[PA];
+#pragma unroll
+            for (int r = 0; r < PA; ++r) a[r] = fp::mul(c.h[0], w[2 * r]);
+#pragma unroll
+            for (int m = 1; m < F; ++m)
+#pragma unroll
+                for (int r = 0; r < PA; ++r) a[r] = fp::mac(a[r], c.h[m], w[2 * r + m]);
+#pragma unroll
+            for (int r = 0; r < PA; ++r) d[r] = fp::mul(c.g[F - 1], w[G::WO + 2 * r]);
+#pragma unroll
+            for (int q = 1; q < F; ++q)
+#pragma unroll
+                for (int r = 0; r < PA; ++r) d[r] = fp::mac(d[r], c.g[F - 1 - q], w[G::WO + 2 * r + q]);
+            store_a(p, a);
+            if constexpr (PA == 2) gstore2(dp, d[0], d[1]); else __stcs(dp, d[0]);
+        }
+    }
+    for (; p < NA; p += step) {
         T w[G::WIN];
         load_window<G::WIN>(w, in + 2 * p);
         T a[PA];
@@ -167,16 +202,6 @@ __device__ __forceinline__ void ana_level(const T *__restrict__ in, int NA, int 
 #pragma unroll
             for (int r = 0; r < PA; ++r) a[r] = fp::mac(a[r], c.h[m], w[2 * r + m]);
         store_a(p, a);
-        if (p < ND) {
-            T d[PA];
-#pragma unroll
-            for (int r = 0; r < PA; ++r) d[r] = fp::mul(c.g[F - 1], w[G::WO + 2 * r]);
-#pragma unroll
-            for (int q = 1; q < F; ++q)
-#pragma unroll
-                for (int r = 0; r < PA; ++r) d[r] = fp::mac(d[r], c.g[F - 1 - q], w[G::WO + 2 * r + q]);
-            store_d(p, d);
-        }
     }
 }
 
@@ -196,16 +221,54 @@ struct SynPlan {
     int poff, qoff;        // ping-pong buffers for a_{K-1} .. a_1
 };
 
-// one synthesis level: two output pairs per thread-iteration
+// one synthesis level
 //   x[2u]   = (sum_{i=u-Q+1..u} h[2(u-i)]   a[i]) + (sum_{i=u..u+Q-1} g[2(i-u)+1] d[i])
 //   x[2u+1] = (sum_{i=u-Q+1..u} h[2(u-i)+1] a[i]) + (sum_{i=u..u+Q-1} g[2(i-u)]   d[i])
 // `abuf[i]` = a_l[s_l + rlo_l + i], `dbuf[i]` = d_l[s_l + dlo_l + i]; outputs a_{l-1}[s_{l-1} + rlo_{l-1} + 2*ur ...]
+// 4-byte samples with 16-byte-aligned windows (oa, od, npairs multiples of 4; Q4 staged samples in front of a[u_first] and
+// behind d[u_last]): FOUR pairs per thread-iteration from 16-byte loads -- 4 LDS.128 per 64 FMA (db4) where the two-pair
+// form below issues 12 LDS.64.  Otherwise two pairs per thread-iteration from 8-byte (Float64: 16-byte) loads.
 template <typename T, int F, bool STRICT, typename SO>
 __device__ __forceinline__ void syn_level(const T *__restrict__ abuf, const T *__restrict__ dbuf, int oa, int od, int npairs,
                                           const Taps<T, F> &c, SO store_out) {
     using fp = FP<STRICT>;
     using G = FGeom<F>;
     constexpr int Q = G::Q;
+    if constexpr (sizeof(T) == 4) {
+        if (((oa | od | npairs) & 3) == 0 && oa >= G::Q4) {
+            constexpr int Q4 = G::Q4;
+            const T *pa = abuf + oa - Q4, *pd = dbuf + od;
+            for (int ur = 4 * threadIdx.x; ur < npairs; ur += 4 * blockDim.x) {
+                T wa[Q4 + 4], wd[Q4 + 4];
+                load_window<Q4 + 4>(wa, pa + ur);
+                load_window<Q4 + 4>(wd, pd + ur);
+                T o[8];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    // a[u' - k] = wa[Q4 + r - k], d[u' + k] = wd[r + k]
+                    T rae = fp::mul(c.h[2 * (Q - 1)], wa[Q4 + r - (Q - 1)]);
+                    T rao = fp::mul(c.h[2 * (Q - 1) + 1], wa[Q4 + r - (Q - 1)]);
+#pragma unroll
+                    for (int k = Q - 2; k >= 0; --k) {
+                        rae = fp::mac(rae, c.h[2 * k], wa[Q4 + r - k]);
+                        rao = fp::mac(rao, c.h[2 * k + 1], wa[Q4 + r - k]);
+                    }
+                    T rde = fp::mul(c.g[1], wd[r]);
+                    T rdo = fp::mul(c.g[0], wd[r]);
+#pragma unroll
+                    for (int k = 1; k < Q; ++k) {
+                        rde = fp::mac(rde, c.g[2 * k + 1], wd[r + k]);
+                        rdo = fp::mac(rdo, c.g[2 * k], wd[r + k]);
+                    }
+                    o[2 * r] = fp::add(rae, rde);
+                    o[2 * r + 1] = fp::add(rao, rdo);
+                }
+                store_out(ur, o[0], o[1], o[2], o[3]);
+                store_out(ur + 2, o[4], o[5], o[6], o[7]);
+            }
+            return;
+        }
+    }
     for (int ur = 2 * threadIdx.x; ur < npairs; ur += 2 * blockDim.x) {
         T wa[G::QA + 2], wd[G::QD];
         load_pairs<G::QA + 2>(wa, abuf + oa + ur - G::QA);
