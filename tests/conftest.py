@@ -34,3 +34,12 @@ def wavelet_class(key):
 
 def rng(seed=42):
     return np.random.default_rng(seed)
+
+
+@pytest.fixture(autouse=True)
+def _seed_torch():
+    """every test starts from the same torch seed (CPU and CUDA generators): inputs drawn with torch.randn are the same on
+    every run, so a result never depends on an unlucky draw (exact magnitude ties, for example)"""
+    import torch
+    torch.manual_seed(1234)
+    yield

@@ -48,5 +48,24 @@ for rnd in range(6):
         for k in keys: os.environ.pop(k, None)
         os.environ.update(env)
         res[name][0].append(timeit(fwd)); res[name][1].append(timeit(inv))
+def kernel_times(fn, reps=5):
+    """per-kernel device ms per call from the library's own event hook (serialises the launches it brackets)"""
+    import ctypes as C
+    from wavelets_b200 import _lib
+    L = _lib.lib()
+    buf = C.create_string_buffer(1 << 14)
+    L.wb200_profile_collect(buf, len(buf))
+    L.wb200_profile_enable(1)
+    for _ in range(reps): fn()
+    torch.cuda.synchronize()
+    L.wb200_profile_enable(0)
+    nb = L.wb200_profile_collect(buf, len(buf))
+    return {ln.split()[0]: (int(ln.split()[1]) // reps, float(ln.split()[2]) / reps) for ln in buf.raw[:nb].decode().splitlines()}
+if os.environ.get("AB_KERNELS"):
+    for name, env in cfgs.items():
+        for k in keys: os.environ.pop(k, None)
+        os.environ.update(env)
+        for lab, fn in (("fwd", fwd), ("inv", inv)):
+            print(f"  [{name}] {lab}: " + ", ".join(f"{k} x{c} {ms:.4f} ms" for k, (c, ms) in kernel_times(fn).items()))
 for name, (f, i) in res.items():
     print(f"{kind:6s} {name:44s} fwd {statistics.median(f):8.4f} ms   inv {statistics.median(i):8.4f} ms   pair {statistics.median(f) + statistics.median(i):8.4f} ms")

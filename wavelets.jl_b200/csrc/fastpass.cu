@@ -15,6 +15,7 @@
 // Arithmetic: the closed forms of filtdown!/filtup! in the reference's summation order; the detail
 // is produced from the same window as the approximation (d[k + F/2 - 1] and a[k] read the same F inputs).
 #include "fused1d_dev.cuh"
+#include <cstring>
 
 namespace wb {
 
@@ -229,8 +230,8 @@ constexpr int WPT_SUB_MAX = 4096;        // default.  r02 sweep (sym8, 2^16, 102
 int wpt_subtree_max_samples(int esize) {
     const char *e = std::getenv("WB200_WPT_SUBMAX");
     int v = (e && *e) ? std::atoi(e) : WPT_SUB_MAX;
-    const int cap = esize == 4 ? 16384 : 8192;        // two ping-pong buffers of m samples: 128 KB of shared memory at most
-    if (v > cap) v = cap;
+    (void)esize;
+    if (v > 8192) v = 8192;
     int p = 2;
     while (p * 2 <= v) p *= 2;               // a power of two
     return p;
@@ -319,7 +320,7 @@ __device__ __forceinline__ void tiny_syn(const T (&a)[NH], const T (&d)[NH], T (
 // compare-and-reset (the division form cost ~110 of the 260 instructions of an iteration).
 template <typename T, int F, bool STRICT, bool P2>
 __device__ __forceinline__ void wpt_sub_ana_chunks(const T *__restrict__ in, T *__restrict__ out, int m, int nh, bool last,
-                                                   const Taps<T, F> &c) {
+                                                   const Taps<T, F> &c, int i0, int i1, int istep) {
     using fp = FP<STRICT>;
     constexpr int Q = F / 2;
     constexpr int CL = (Q - 1 + 3) / 4;          // chunks of reach; DS = 4 CL
@@ -328,7 +329,7 @@ __device__ __forceinline__ void wpt_sub_ana_chunks(const T *__restrict__ in, T *
     const int mh = m >> 1, hh = nh >> 1, ml = nh << 1;
     const int cpn = nh >> 2;
     const int sh = P2 ? (31 - __clz(cpn)) : 0, mask = cpn - 1;
-    for (int idx = threadIdx.x; idx < (m >> 3); idx += blockDim.x) {
+    for (int idx = i0; idx < i1; idx += istep) {
         int j, c0;
         if constexpr (P2) { j = idx >> sh; c0 = idx & mask; } else { j = idx / cpn; c0 = idx - j * cpn; }
         const T *E = in + j * nh, *O = E + mh;
@@ -374,14 +375,15 @@ __device__ __forceinline__ void wpt_sub_ana_chunks(const T *__restrict__ in, T *
 
 // One synthesis level of band-split sub-nodes (a_j at [j nh), d_j at m/2 + [j nh)); see wpt_sub_ana_chunks for P2.
 template <typename T, int F, bool STRICT, bool P2>
-__device__ __forceinline__ void wpt_sub_syn_chunks(const T *__restrict__ in, T *__restrict__ out, int m, int nh, const Taps<T, F> &c) {
+__device__ __forceinline__ void wpt_sub_syn_chunks(const T *__restrict__ in, T *__restrict__ out, int m, int nh, const Taps<T, F> &c,
+                                                   int i0, int i1, int istep) {
     using fp = FP<STRICT>;
     constexpr int Q = F / 2;
     constexpr int CL = (Q - 1 + 3) / 4;
     const int mh = m >> 1, ml = nh << 1;
     const int cpn = nh >> 2;
     const int sh = P2 ? (31 - __clz(cpn)) : 0, mask = cpn - 1;
-    for (int idx = threadIdx.x; idx < (m >> 3); idx += blockDim.x) {
+    for (int idx = i0; idx < i1; idx += istep) {
         int j, c0;
         if constexpr (P2) { j = idx >> sh; c0 = idx & mask; } else { j = idx / cpn; c0 = idx - j * cpn; }
         const T *A = in + j * nh, *Dd = A + mh;
@@ -431,6 +433,73 @@ __device__ __forceinline__ void wpt_sub_syn_chunks(const T *__restrict__ in, T *
     }
 }
 
+// FAST mode, trees that go all the way down (final nodes of one sample): the last four levels of a 16-sample node --
+// node lengths 16, 8, 4, 2, every filter wrapped round the node several times -- are ONE fixed 16 x 16 linear map.  The host
+// composes it in double precision from the same taps (leaf16_matrices); a thread then takes a whole node: 256 FMAs on
+// constant-bank coefficients instead of 4 levels x 16 taps x 16 outputs = 1024 (sym8: a quarter of the subtree's arithmetic
+// gone), no barriers, and the leaves go straight to HBM.  STRICT keeps the level-by-level reference order.
+template <typename T> struct Leaf16 { T m[16][16]; };      // out[r] = sum_c m[r][c] in[c], both in natural order
+
+// analysis: `in` holds the 16-sample nodes split (E_j at [8 j), O_j at m/2 + [8 j)); leaves of node j -> D[16 j ..]
+template <typename T>
+__device__ __forceinline__ void leaf16_ana(const T *__restrict__ in, T *__restrict__ D, int m, const Leaf16<T> &M) {
+    const int mh = m >> 1;
+    // one node per thread, NOT a loop: inside a loop the compiler hoists the 256 loop-invariant coefficients out of the constant
+    // bank into registers and spills them; straight-line code reads them as FFMA constant operands.  (m / 16 <= blockDim.x: host)
+    const int j = threadIdx.x;
+    if (j < (m >> 4)) {
+        T e[8], o[8];
+        { T t4[4]; ld4(t4, in + 8 * j); e[0] = t4[0]; e[1] = t4[1]; e[2] = t4[2]; e[3] = t4[3];
+          ld4(t4, in + 8 * j + 4); e[4] = t4[0]; e[5] = t4[1]; e[6] = t4[2]; e[7] = t4[3];
+          ld4(t4, in + mh + 8 * j); o[0] = t4[0]; o[1] = t4[1]; o[2] = t4[2]; o[3] = t4[3];
+          ld4(t4, in + mh + 8 * j + 4); o[4] = t4[0]; o[5] = t4[1]; o[6] = t4[2]; o[7] = t4[3]; }
+#pragma unroll
+        for (int r0 = 0; r0 < 16; r0 += 4) {
+            T y[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                T acc = M.m[r0 + r][0] * e[0];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i > 0) acc = fma(M.m[r0 + r][2 * i], e[i], acc);
+                    acc = fma(M.m[r0 + r][2 * i + 1], o[i], acc);
+                }
+                y[r] = acc;
+            }
+            if constexpr (sizeof(T) == 4) __stcs(reinterpret_cast<float4 *>(D + 16 * j + r0), make_float4(y[0], y[1], y[2], y[3]));
+            else { __stcs(reinterpret_cast<double2 *>(D + 16 * j + r0), make_double2(y[0], y[1])); __stcs(reinterpret_cast<double2 *>(D + 16 * j + r0 + 2), make_double2(y[2], y[3])); }
+        }
+    }
+}
+// synthesis: leaves of node j from S[16 j ..]; the rebuilt 16-sample node is band (j & 1) of its parent j >> 1 in the
+// band-split layout of the next (32-sample) level, or -- a 16-sample subtree -- the output itself
+template <typename T>
+__device__ __forceinline__ void leaf16_syn(const T *__restrict__ S, T *__restrict__ out, int m, const Leaf16<T> &M) {
+    const int mh = m >> 1;
+    const int j = threadIdx.x;                   // one node per thread (see leaf16_ana)
+    if (j < (m >> 4)) {
+        T y[16];
+#pragma unroll
+        for (int r0 = 0; r0 < 16; r0 += 4) {
+            if constexpr (sizeof(T) == 4) { const float4 v = __ldcs(reinterpret_cast<const float4 *>(S + 16 * j + r0)); y[r0] = v.x; y[r0 + 1] = v.y; y[r0 + 2] = v.z; y[r0 + 3] = v.w; }
+            else { const double2 v0 = __ldcs(reinterpret_cast<const double2 *>(S + 16 * j + r0)), v1 = __ldcs(reinterpret_cast<const double2 *>(S + 16 * j + r0 + 2)); y[r0] = v0.x; y[r0 + 1] = v0.y; y[r0 + 2] = v1.x; y[r0 + 3] = v1.y; }
+        }
+        T *o = (m == 16) ? out : out + (j & 1) * mh + (j >> 1) * 16;
+#pragma unroll
+        for (int c0 = 0; c0 < 16; c0 += 4) {
+            T x[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                T acc = M.m[c0 + cc][0] * y[0];
+#pragma unroll
+                for (int r = 1; r < 16; ++r) acc = fma(M.m[c0 + cc][r], y[r], acc);
+                x[cc] = acc;
+            }
+            st4(o + c0, x[0], x[1], x[2], x[3]);
+        }
+    }
+}
+
 // Shared-memory layouts (both kernels ping-pong between two m-sample buffers):
 //   analysis input of a level  : every sub-node SPLIT into its polyphase components, all even parts first --
 //        node j (length ml, nh = ml/2): E_j at [j nh, (j+1) nh), O_j at m/2 + [j nh, (j+1) nh).  A warp's 16-byte loads are
@@ -439,9 +508,9 @@ __device__ __forceinline__ void wpt_sub_syn_chunks(const T *__restrict__ in, T *
 //   synthesis input of a level : all approximation bands first -- a_j at [j nh, ..), d_j at m/2 + [j nh, ..);
 //   the last analysis level writes, and the first synthesis level reads, the natural packet order [a_j | d_j] per node.
 template <typename T, int F, bool STRICT>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256, 5)
 k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int levels, int64_t nodes,
-              const __grid_constant__ Taps<T, F> c) {
+              const __grid_constant__ Taps<T, F> c, int leaf16, int wsync, const __grid_constant__ Leaf16<T> M16) {
     using fp = FP<STRICT>;
     constexpr int Q = F / 2;
     constexpr int CL = (Q - 1 + 3) / 4;          // chunks of left / right reach
@@ -457,15 +526,29 @@ k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
         in[mh + p] = S[base + 2 * p + 1];
     }
     __syncthreads();
-    for (int l = 0; l < levels; ++l) {
+    const int lv_end = leaf16 ? levels - 4 : levels;          // leaf16: the 16-sample nodes finish in one matrix stage
+    // Once a level has at least as many nodes as the CTA has warps, every warp owns whole nodes -- and a node's children live in
+    // the shared-memory ranges of the node itself -- so consecutive such levels need only a WARP barrier between them: the
+    // eight warps of a CTA drift apart instead of meeting at a block barrier per level.
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto warp_local = [&](int l) {
+        if (l < 0 || l >= lv_end || !wsync) return false;
+        const int nodes_l = 1 << l, nh = (m >> l) >> 1;
+        return nh >= 4 && (nh & 3) == 0 && nodes_l >= nwarps && (nodes_l % nwarps) == 0 && ((m >> 3) % nwarps) == 0;
+    };
+    for (int l = 0; l < lv_end; ++l) {
         const int ml = m >> l, nh = ml >> 1;
         const bool last = (l == levels - 1);
         const int hh = nh >> 1;                               // half length of a child (the next level's nh)
         // child cidx (2j: approximation, 2j+1: detail) of the next level: E' at cidx*hh, O' at mh + cidx*hh
         if (nh >= 4 && (nh & 3) == 0) {
             const int cpn = nh >> 2;                          // 16-byte chunks per component of a sub-node
-            if ((cpn & (cpn - 1)) == 0) wpt_sub_ana_chunks<T, F, STRICT, true>(in, out, m, nh, last, c);
-            else wpt_sub_ana_chunks<T, F, STRICT, false>(in, out, m, nh, last, c);
+            // warp-local level: the warp walks its own whole nodes (contiguous idx range), so only a warp barrier follows
+            const bool wl = warp_local(l);
+            const int per = (m >> 3) / nwarps;
+            const int i0 = wl ? warp * per + lane : (int)threadIdx.x, i1 = wl ? (warp + 1) * per : (m >> 3), istep = wl ? 32 : (int)blockDim.x;
+            if ((cpn & (cpn - 1)) == 0) wpt_sub_ana_chunks<T, F, STRICT, true>(in, out, m, nh, last, c, i0, i1, istep);
+            else wpt_sub_ana_chunks<T, F, STRICT, false>(in, out, m, nh, last, c, i0, i1, istep);
         } else if (ml == 4) {
             for (int j = threadIdx.x; j < (m >> 2); j += blockDim.x) {
                 const T xe[2] = {in[2 * j], in[2 * j + 1]}, xo[2] = {in[mh + 2 * j], in[mh + 2 * j + 1]};
@@ -510,16 +593,17 @@ k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
                 }
             }
         }
-        __syncthreads();
+        if (warp_local(l) && warp_local(l + 1)) __syncwarp(); else __syncthreads();
         T *t = in; in = out; out = t;
     }
+    if (leaf16) { leaf16_ana<T>(in, D + base, m, M16); return; }
     for (int i = threadIdx.x; i < m; i += blockDim.x) D[base + i] = in[i];
 }
 
 template <typename T, int F, bool STRICT>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256, 5)
 k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int levels, int64_t nodes,
-              const __grid_constant__ Taps<T, F> c) {
+              const __grid_constant__ Taps<T, F> c, int leaf16, int wsync, const __grid_constant__ Leaf16<T> M16) {
     using fp = FP<STRICT>;
     constexpr int Q = F / 2;
     constexpr int CL = (Q - 1 + 3) / 4;
@@ -529,7 +613,9 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
     const int mh = m >> 1;
     const int64_t q = blockIdx.x % nodes, b = blockIdx.x / nodes;
     const int64_t base = b * n + q * (int64_t)m;
-    {   // natural packet order -> band-split: node j of the deepest level: a_j to [j nh), d_j to mh + [j nh)
+    if (leaf16) {
+        leaf16_syn<T>(S + base, in, m, M16);      // leaves -> 16-sample nodes, already in the band-split layout of the 32-sample level
+    } else {   // natural packet order -> band-split: node j of the deepest level: a_j to [j nh), d_j to mh + [j nh)
         const int ml = m >> (levels - 1), nh = ml >> 1;
         for (int i = threadIdx.x; i < m; i += blockDim.x) {
             const int j = i / ml, r = i - j * ml;
@@ -537,13 +623,24 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
         }
     }
     __syncthreads();
-    for (int l = levels - 1; l >= 0; --l) {
+    const int lv_first = leaf16 ? levels - 5 : levels - 1;
+    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // see k_wpt_sub_ana: a warp that owns whole nodes of level l wrote exactly the bands of its own nodes of level l - 1
+    auto warp_local = [&](int l) {
+        if (l < 0 || l > lv_first || !wsync) return false;
+        const int nodes_l = 1 << l, nh = (m >> l) >> 1;
+        return nh >= 4 && (nh & 3) == 0 && nodes_l >= nwarps && (nodes_l % nwarps) == 0 && ((m >> 3) % nwarps) == 0;
+    };
+    for (int l = lv_first; l >= 0; --l) {
         const int ml = m >> l, nh = ml >> 1;
         // node j's output (ml samples) is band (j & 1) of its parent j >> 1 for the next, shallower level
         if (nh >= 4 && (nh & 3) == 0) {
             const int cpn = nh >> 2;
-            if ((cpn & (cpn - 1)) == 0) wpt_sub_syn_chunks<T, F, STRICT, true>(in, out, m, nh, c);
-            else wpt_sub_syn_chunks<T, F, STRICT, false>(in, out, m, nh, c);
+            const bool own = warp_local(l);
+            const int per = (m >> 3) / nwarps;
+            const int i0 = own ? warp * per + lane : (int)threadIdx.x, i1 = own ? (warp + 1) * per : (m >> 3), istep = own ? 32 : (int)blockDim.x;
+            if ((cpn & (cpn - 1)) == 0) wpt_sub_syn_chunks<T, F, STRICT, true>(in, out, m, nh, c, i0, i1, istep);
+            else wpt_sub_syn_chunks<T, F, STRICT, false>(in, out, m, nh, c, i0, i1, istep);
         } else if (ml == 4) {
             for (int j = threadIdx.x; j < (m >> 2); j += blockDim.x) {
                 const T a[2] = {in[2 * j], in[2 * j + 1]}, d[2] = {in[mh + 2 * j], in[mh + 2 * j + 1]};
@@ -586,10 +683,55 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
                 o[2 * u + 1] = fp::add(rao, rdo);
             }
         }
-        __syncthreads();
+        if (warp_local(l) && warp_local(l - 1)) __syncwarp(); else __syncthreads();
         T *t = in; in = out; out = t;
     }
     for (int i = threadIdx.x; i < m; i += blockDim.x) D[base + i] = in[i];
+}
+
+// the 16 x 16 maps of leaf16_ana / leaf16_syn: four periodic packet levels of a 16-sample node (natural order), composed in
+// double precision from the taps as the kernels hold them (rounded to T)
+template <typename T>
+static void leaf16_matrices(const FilterCoefs<T> &fc, Leaf16<T> &A, Leaf16<T> &Sy) {
+    const int F = fc.F, Q = F / 2;
+    auto ana = [&](const double *x, int ml, double *y) {          // one level: y = [a | d]
+        const int nh = ml / 2;
+        for (int k = 0; k < nh; ++k) {
+            double a = 0, d = 0;
+            for (int t = 0; t < F; ++t) {
+                a += (double)fc.h[t] * x[(2 * k + t) % ml];
+                d += (double)fc.g[F - 1 - t] * x[(((2 * k + 2 - F + t) % ml) + ml) % ml];
+            }
+            y[k] = a; y[nh + k] = d;
+        }
+    };
+    auto syn = [&](const double *a, const double *d, int nh, double *x) {
+        for (int u = 0; u < nh; ++u) {
+            double e = 0, o = 0;
+            for (int t = 0; t < Q; ++t) {
+                const double av = a[(((u - t) % nh) + nh) % nh], dv = d[(u + t) % nh];
+                e += (double)fc.h[2 * t] * av + (double)fc.g[2 * t + 1] * dv;
+                o += (double)fc.h[2 * t + 1] * av + (double)fc.g[2 * t] * dv;
+            }
+            x[2 * u] = e; x[2 * u + 1] = o;
+        }
+    };
+    for (int c = 0; c < 16; ++c) {
+        double cur[16] = {0}, nxt[16];
+        cur[c] = 1.0;
+        for (int ml = 16; ml >= 2; ml >>= 1) {                    // analysis of the unit vector e_c: column c of A
+            for (int j = 0; j < 16 / ml; ++j) ana(cur + j * ml, ml, nxt + j * ml);
+            for (int i = 0; i < 16; ++i) cur[i] = nxt[i];
+        }
+        for (int r = 0; r < 16; ++r) A.m[r][c] = (T)cur[r];
+        double y[16] = {0};
+        y[c] = 1.0;
+        for (int ml = 2; ml <= 16; ml <<= 1) {                    // synthesis of the unit leaf vector e_c: column c of Sy
+            for (int j = 0; j < 16 / ml; ++j) syn(y + j * ml, y + j * ml + ml / 2, ml / 2, nxt + j * ml);
+            for (int i = 0; i < 16; ++i) y[i] = nxt[i];
+        }
+        for (int r = 0; r < 16; ++r) Sy.m[r][c] = (T)y[r];
+    }
 }
 
 template <typename T, int F, bool STRICT>
@@ -600,20 +742,27 @@ static int wpt_sub_F(const T *S, T *D, int64_t n, int m, int levels, int64_t nod
     const int64_t nblk = nodes * B;
     if (nblk > 0x7fffffffLL) return 0;
     const size_t smem = (size_t)2 * m * sizeof(T);
-    // two thread-iterations per level: a node of 4096 samples runs 256 threads (six CTAs per SM), 8192 -> 512, 16384 -> 1024
-    int nthr = env_int_fp("WB200_WPT_SUB_NT", 0);
-    if (nthr < 32 || nthr > 1024) nthr = m >= 16384 ? 1024 : (m >= 8192 ? 512 : 256);
+    // 256 threads: two thread-iterations per level of a 4096-sample node, six CTAs per SM (r02 A/B: 8192-sample nodes with 512
+    // threads 2.26 ms, 16384 with 1024 threads 2.07 ms against 2.08 ms per 1024 signals -- no gain, so the CTA stays small)
+    int nthr = env_int_fp("WB200_WPT_SUB_NT", 256);
+    if (nthr < 32 || nthr > 256) nthr = 256;
     nthr &= ~31;
+    // fast mode, full-depth tree, 16-byte granular rows: the last four levels as one 16 x 16 map per node
+    const bool leaf16 = !STRICT && levels >= 4 && ((int64_t)m >> levels) == 1 && (m >> 4) <= nthr && env_int_fp("WB200_WPT_LEAF16", 1) != 0 &&
+                        ((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(D)) & 15) == 0 && ((n * (int64_t)sizeof(T)) % 16) == 0;
+    const int wsync = env_int_fp("WB200_WPT_WARPSYNC", 1) != 0 ? 1 : 0;      // warp barriers between warp-local levels
+    Leaf16<T> MA, MS;
+    if (leaf16) leaf16_matrices<T>(fc, MA, MS); else { std::memset(&MA, 0, sizeof(MA)); std::memset(&MS, 0, sizeof(MS)); }
     if (fw) {
         auto kern = k_wpt_sub_ana<T, F, STRICT>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
         LaunchScope scope("wpt_subtree_analysis", st);
-        kern<<<(unsigned)nblk, nthr, smem, st>>>(S, D, n, m, levels, nodes, taps);
+        kern<<<(unsigned)nblk, nthr, smem, st>>>(S, D, n, m, levels, nodes, taps, leaf16 ? 1 : 0, wsync, MA);
     } else {
         auto kern = k_wpt_sub_syn<T, F, STRICT>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
         LaunchScope scope("wpt_subtree_synthesis", st);
-        kern<<<(unsigned)nblk, nthr, smem, st>>>(S, D, n, m, levels, nodes, taps);
+        kern<<<(unsigned)nblk, nthr, smem, st>>>(S, D, n, m, levels, nodes, taps, leaf16 ? 1 : 0, wsync, MS);
     }
     return check_launch("wpt_subtree") ? 1 : -1;
 }

@@ -228,74 +228,89 @@ struct SynPlan {
 // 4-byte samples with 16-byte-aligned windows (oa, od, npairs multiples of 4; Q4 staged samples in front of a[u_first] and
 // behind d[u_last]): FOUR pairs per thread-iteration from 16-byte loads -- 4 LDS.128 per 64 FMA (db4) where the two-pair
 // form below issues 12 LDS.64.  Otherwise two pairs per thread-iteration from 8-byte (Float64: 16-byte) loads.
+// four output pairs ur .. ur+3 (4-byte samples): pa = abuf + oa - Q4, pd = dbuf + od, both 16-byte aligned, ur a multiple of 4
 template <typename T, int F, bool STRICT, typename SO>
-__device__ __forceinline__ void syn_level(const T *__restrict__ abuf, const T *__restrict__ dbuf, int oa, int od, int npairs,
-                                          const Taps<T, F> &c, SO store_out) {
+__device__ __forceinline__ void syn_quad(const T *__restrict__ pa, const T *__restrict__ pd, int ur, const Taps<T, F> &c, SO store_out) {
+    using fp = FP<STRICT>;
+    using G = FGeom<F>;
+    constexpr int Q = G::Q, Q4 = G::Q4;
+    T wa[Q4 + 4], wd[Q4 + 4];
+    load_window<Q4 + 4>(wa, pa + ur);
+    load_window<Q4 + 4>(wd, pd + ur);
+    T o[8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        // a[u' - k] = wa[Q4 + r - k], d[u' + k] = wd[r + k]
+        T rae = fp::mul(c.h[2 * (Q - 1)], wa[Q4 + r - (Q - 1)]);
+        T rao = fp::mul(c.h[2 * (Q - 1) + 1], wa[Q4 + r - (Q - 1)]);
+#pragma unroll
+        for (int k = Q - 2; k >= 0; --k) {
+            rae = fp::mac(rae, c.h[2 * k], wa[Q4 + r - k]);
+            rao = fp::mac(rao, c.h[2 * k + 1], wa[Q4 + r - k]);
+        }
+        T rde = fp::mul(c.g[1], wd[r]);
+        T rdo = fp::mul(c.g[0], wd[r]);
+#pragma unroll
+        for (int k = 1; k < Q; ++k) {
+            rde = fp::mac(rde, c.g[2 * k + 1], wd[r + k]);
+            rdo = fp::mac(rdo, c.g[2 * k], wd[r + k]);
+        }
+        o[2 * r] = fp::add(rae, rde);
+        o[2 * r + 1] = fp::add(rao, rdo);
+    }
+    store_out(ur, o[0], o[1], o[2], o[3]);
+    store_out(ur + 2, o[4], o[5], o[6], o[7]);
+}
+// two output pairs ur, ur+1: pa = abuf + oa - QA, pd = dbuf + od (8-byte aligned for 4-byte samples, 16 for 8-byte), ur even
+template <typename T, int F, bool STRICT, typename SO>
+__device__ __forceinline__ void syn_duo(const T *__restrict__ pa, const T *__restrict__ pd, int ur, const Taps<T, F> &c, SO store_out) {
     using fp = FP<STRICT>;
     using G = FGeom<F>;
     constexpr int Q = G::Q;
+    T wa[G::QA + 2], wd[G::QD];
+    load_pairs<G::QA + 2>(wa, pa + ur);
+    load_pairs<G::QD>(wd, pd + ur);
+    T o[4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        // a[u' - k] = wa[QA + r - k], d[u' + k] = wd[r + k]
+        T rae = fp::mul(c.h[2 * (Q - 1)], wa[G::QA + r - (Q - 1)]);
+        T rao = fp::mul(c.h[2 * (Q - 1) + 1], wa[G::QA + r - (Q - 1)]);
+#pragma unroll
+        for (int k = Q - 2; k >= 0; --k) {
+            rae = fp::mac(rae, c.h[2 * k], wa[G::QA + r - k]);
+            rao = fp::mac(rao, c.h[2 * k + 1], wa[G::QA + r - k]);
+        }
+        T rde = fp::mul(c.g[1], wd[r]);
+        T rdo = fp::mul(c.g[0], wd[r]);
+#pragma unroll
+        for (int k = 1; k < Q; ++k) {
+            rde = fp::mac(rde, c.g[2 * k + 1], wd[r + k]);
+            rdo = fp::mac(rdo, c.g[2 * k], wd[r + k]);
+        }
+        o[2 * r] = fp::add(rae, rde);
+        o[2 * r + 1] = fp::add(rao, rdo);
+    }
+    store_out(ur, o[0], o[1], o[2], o[3]);
+}
+// whether a level can run the four-pair form
+template <typename T, int F> __device__ __forceinline__ bool syn_quad_ok(int oa, int od, int npairs) {
+    return sizeof(T) == 4 && ((oa | od | npairs) & 3) == 0 && oa >= FGeom<F>::Q4;
+}
+
+template <typename T, int F, bool STRICT, typename SO>
+__device__ __forceinline__ void syn_level(const T *__restrict__ abuf, const T *__restrict__ dbuf, int oa, int od, int npairs,
+                                          const Taps<T, F> &c, SO store_out) {
+    using G = FGeom<F>;
     if constexpr (sizeof(T) == 4) {
-        if (((oa | od | npairs) & 3) == 0 && oa >= G::Q4) {
-            constexpr int Q4 = G::Q4;
-            const T *pa = abuf + oa - Q4, *pd = dbuf + od;
-            for (int ur = 4 * threadIdx.x; ur < npairs; ur += 4 * blockDim.x) {
-                T wa[Q4 + 4], wd[Q4 + 4];
-                load_window<Q4 + 4>(wa, pa + ur);
-                load_window<Q4 + 4>(wd, pd + ur);
-                T o[8];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    // a[u' - k] = wa[Q4 + r - k], d[u' + k] = wd[r + k]
-                    T rae = fp::mul(c.h[2 * (Q - 1)], wa[Q4 + r - (Q - 1)]);
-                    T rao = fp::mul(c.h[2 * (Q - 1) + 1], wa[Q4 + r - (Q - 1)]);
-#pragma unroll
-                    for (int k = Q - 2; k >= 0; --k) {
-                        rae = fp::mac(rae, c.h[2 * k], wa[Q4 + r - k]);
-                        rao = fp::mac(rao, c.h[2 * k + 1], wa[Q4 + r - k]);
-                    }
-                    T rde = fp::mul(c.g[1], wd[r]);
-                    T rdo = fp::mul(c.g[0], wd[r]);
-#pragma unroll
-                    for (int k = 1; k < Q; ++k) {
-                        rde = fp::mac(rde, c.g[2 * k + 1], wd[r + k]);
-                        rdo = fp::mac(rdo, c.g[2 * k], wd[r + k]);
-                    }
-                    o[2 * r] = fp::add(rae, rde);
-                    o[2 * r + 1] = fp::add(rao, rdo);
-                }
-                store_out(ur, o[0], o[1], o[2], o[3]);
-                store_out(ur + 2, o[4], o[5], o[6], o[7]);
-            }
+        if (syn_quad_ok<T, F>(oa, od, npairs)) {
+            const T *pa = abuf + oa - G::Q4, *pd = dbuf + od;
+            for (int ur = 4 * threadIdx.x; ur < npairs; ur += 4 * blockDim.x) syn_quad<T, F, STRICT>(pa, pd, ur, c, store_out);
             return;
         }
     }
-    for (int ur = 2 * threadIdx.x; ur < npairs; ur += 2 * blockDim.x) {
-        T wa[G::QA + 2], wd[G::QD];
-        load_pairs<G::QA + 2>(wa, abuf + oa + ur - G::QA);
-        load_pairs<G::QD>(wd, dbuf + od + ur);
-        T o[4];
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            // a[u' - k] = wa[QA + r - k], d[u' + k] = wd[r + k]
-            T rae = fp::mul(c.h[2 * (Q - 1)], wa[G::QA + r - (Q - 1)]);
-            T rao = fp::mul(c.h[2 * (Q - 1) + 1], wa[G::QA + r - (Q - 1)]);
-#pragma unroll
-            for (int k = Q - 2; k >= 0; --k) {
-                rae = fp::mac(rae, c.h[2 * k], wa[G::QA + r - k]);
-                rao = fp::mac(rao, c.h[2 * k + 1], wa[G::QA + r - k]);
-            }
-            T rde = fp::mul(c.g[1], wd[r]);
-            T rdo = fp::mul(c.g[0], wd[r]);
-#pragma unroll
-            for (int k = 1; k < Q; ++k) {
-                rde = fp::mac(rde, c.g[2 * k + 1], wd[r + k]);
-                rdo = fp::mac(rdo, c.g[2 * k], wd[r + k]);
-            }
-            o[2 * r] = fp::add(rae, rde);
-            o[2 * r + 1] = fp::add(rao, rdo);
-        }
-        store_out(ur, o[0], o[1], o[2], o[3]);
-    }
+    const T *pa = abuf + oa - G::QA, *pd = dbuf + od;
+    for (int ur = 2 * threadIdx.x; ur < npairs; ur += 2 * blockDim.x) syn_duo<T, F, STRICT>(pa, pd, ur, c, store_out);
 }
 
 

@@ -98,48 +98,54 @@ k_pkt_ana(const T *__restrict__ src, T *__restrict__ dst, int64_t n, int64_t nj,
     const int step = PA * blockDim.x;
     const T *in = bufA;
     T *out = bufB;
+    // every level walks the flattened (band, pair group) index so that all threads stay busy when a band has fewer pair
+    // groups than the CTA has threads (level 4 of a 4096-sample tile: 128 groups per band, 8 parent bands)
+    const int nt = blockDim.x;
     for (int l = 1; l < K; ++l) {
-        const int nb = 1 << (l - 1), NAl = pl.NA[l], Sp = pl.S[l - 1], Sl = pl.S[l];
-        for (int bb = 0; bb < nb; ++bb) {
+        const int nb = 1 << (l - 1), cnt = pl.NA[l] / PA, Sp = pl.S[l - 1], Sl = pl.S[l];
+        int bb = threadIdx.x / cnt, it = threadIdx.x - bb * cnt;
+        while (bb < nb) {
+            const int p = PA * it;
             const T *ib = in + bb * Sp;
             T *oa = out + (2 * bb) * Sl, *od = oa + Sl;
-            for (int p = PA * threadIdx.x; p < NAl; p += step) {
-                T a[PA], d[PA];
-                pkt_pairs<T, F, STRICT, PA>(ib + 2 * p, c, a, d);
-                if constexpr (PA == 2) { store2(oa + p, a[0], a[1]); store2(od + p, d[0], d[1]); }
-                else { oa[p] = a[0]; od[p] = d[0]; }
-            }
+            T a[PA], d[PA];
+            pkt_pairs<T, F, STRICT, PA>(ib + 2 * p, c, a, d);
+            if constexpr (PA == 2) { store2(oa + p, a[0], a[1]); store2(od + p, d[0], d[1]); }
+            else { oa[p] = a[0]; od[p] = d[0]; }
+            it += nt;
+            while (it >= cnt) { it -= cnt; ++bb; }
         }
         __syncthreads();
         const T *tt = in; in = out; out = const_cast<T *>(tt);
     }
     // last level: bands 2bb, 2bb+1 of level K go to HBM, each rotated by its accumulated detail shift
     {
-        const int nb = 1 << (K - 1), ND = pl.NA[K], Sp = pl.S[K - 1];
+        const int nb = 1 << (K - 1), cnt = pl.NA[K] / PA, Sp = pl.S[K - 1];
         const int64_t lenK = nj >> K, sK = s >> K;
-        for (int bb = 0; bb < nb; ++bb) {
+        int bb = threadIdx.x / cnt, it = threadIdx.x - bb * cnt;
+        while (bb < nb) {
             int op = 0;                                   // offset of the parent band bb (level K-1): sum of its detail bits' shifts
             for (int i = K - 2; i >= 0; --i) op = (op >> 1) + (((bb >> i) & 1) ? G::DS : 0);
             // children: o = op/2 (approximation), op/2 + DS (detail); band beta lives at onode + beta*lenK, sample index mod lenK
             const int64_t sa = (sK + (op >> 1)) % lenK, sd = (sK + (op >> 1) + G::DS) % lenK;
             T *pa = onode + (int64_t)(2 * bb) * lenK, *pd = pa + lenK;
-            const T *ib = in + bb * Sp;
             const bool vec = PA == 1 || (((sa | sd) & 1) == 0);   // even starts: the pair stores stay 8-byte aligned and never straddle the wrap
-            for (int p = PA * threadIdx.x; p < ND; p += step) {
-                T a[PA], d[PA];
-                pkt_pairs<T, F, STRICT, PA>(ib + 2 * p, c, a, d);
-                int64_t ia = sa + p, id = sd + p;
-                if (ia >= lenK) ia -= lenK;
-                if (id >= lenK) id -= lenK;
-                if constexpr (PA == 2) {
-                    if (vec) { gstore2(pa + ia, a[0], a[1]); gstore2(pd + id, d[0], d[1]); }
-                    else {
-                        const int64_t ia1 = ia + 1 >= lenK ? ia + 1 - lenK : ia + 1, id1 = id + 1 >= lenK ? id + 1 - lenK : id + 1;
-                        __stcs(pa + ia, a[0]); __stcs(pa + ia1, a[1]);
-                        __stcs(pd + id, d[0]); __stcs(pd + id1, d[1]);
-                    }
-                } else { __stcs(pa + ia, a[0]); __stcs(pd + id, d[0]); }
-            }
+            const int p = PA * it;
+            T a[PA], d[PA];
+            pkt_pairs<T, F, STRICT, PA>(in + bb * Sp + 2 * p, c, a, d);
+            int64_t ia = sa + p, id = sd + p;
+            if (ia >= lenK) ia -= lenK;
+            if (id >= lenK) id -= lenK;
+            if constexpr (PA == 2) {
+                if (vec) { gstore2(pa + ia, a[0], a[1]); gstore2(pd + id, d[0], d[1]); }
+                else {
+                    const int64_t ia1 = ia + 1 >= lenK ? ia + 1 - lenK : ia + 1, id1 = id + 1 >= lenK ? id + 1 - lenK : id + 1;
+                    __stcs(pa + ia, a[0]); __stcs(pa + ia1, a[1]);
+                    __stcs(pd + id, d[0]); __stcs(pd + id1, d[1]);
+                }
+            } else { __stcs(pa + ia, a[0]); __stcs(pd + id, d[0]); }
+            it += nt;
+            while (it >= cnt) { it -= cnt; ++bb; }
         }
     }
 }
@@ -173,23 +179,36 @@ k_pkt_syn(const T *__restrict__ src, T *__restrict__ dst, int64_t n, int64_t nj,
 
     const T *in = bufP;
     T *out = bufQ;
+    using G = FGeom<F>;
+    const int nt = blockDim.x;
     for (int l = K; l >= 1; --l) {
         const int nb = 1 << (l - 1), Sl = pl.S[l];
         const int npairs = (pl.hi[l - 1] - pl.lo[l - 1]) >> 1;
         const int oa = (pl.lo[l - 1] >> 1) - pl.lo[l];                     // index of the first output pair's a / d inside a band buffer
-        if (l > 1) {
-            const int So = pl.S[l - 1];
-            for (int bb = 0; bb < nb; ++bb) {
-                T *ob = out + bb * So;
-                auto so = [&](int ur, T o0, T o1, T o2, T o3) { store4(ob + 2 * ur, o0, o1, o2, o3); };
-                syn_level<T, F, STRICT>(in + (2 * bb) * Sl, in + (2 * bb + 1) * Sl, oa, oa, npairs, c, so);
+        // flattened (band, pair group) walk: a level-K band of a 4096-sample tile has 68 four-pair groups, far fewer than threads
+        const bool quad = syn_quad_ok<T, F>(oa, oa, npairs);
+        const int per = quad ? 4 : 2, cnt = npairs / per;
+        const int back = quad ? G::Q4 : G::QA;
+        const int So = l > 1 ? pl.S[l - 1] : 0;
+        T *o0 = oline + s;
+        int bb = threadIdx.x / cnt, it = threadIdx.x - bb * cnt;
+        while (bb < nb) {
+            const T *pa = in + (2 * bb) * Sl + oa - back, *pd = in + (2 * bb + 1) * Sl + oa;
+            T *ob = out + bb * So;
+            auto so = [&](int ur, T v0, T v1, T v2, T v3) {
+                if (l > 1) store4(ob + 2 * ur, v0, v1, v2, v3); else gstore4(o0 + 2 * ur, v0, v1, v2, v3);
+            };
+            if constexpr (sizeof(T) == 4) {
+                if (quad) syn_quad<T, F, STRICT>(pa, pd, 4 * it, c, so); else syn_duo<T, F, STRICT>(pa, pd, 2 * it, c, so);
+            } else {
+                syn_duo<T, F, STRICT>(pa, pd, 2 * it, c, so);
             }
+            it += nt;
+            while (it >= cnt) { it -= cnt; ++bb; }
+        }
+        if (l > 1) {
             __syncthreads();
             const T *tt = in; in = out; out = const_cast<T *>(tt);
-        } else {
-            T *o = oline + s;
-            auto so = [&](int ur, T o0, T o1, T o2, T o3) { gstore4(o + 2 * ur, o0, o1, o2, o3); };
-            syn_level<T, F, STRICT>(in, in + Sl, oa, oa, npairs, c, so);
         }
     }
 }
