@@ -320,7 +320,7 @@ __device__ __forceinline__ void tiny_syn(const T (&a)[NH], const T (&d)[NH], T (
 // compare-and-reset (the division form cost ~110 of the 260 instructions of an iteration).
 template <typename T, int F, bool STRICT, bool P2>
 __device__ __forceinline__ void wpt_sub_ana_chunks(const T *__restrict__ in, T *__restrict__ out, int m, int nh, bool last,
-                                                   const Taps<T, F> &c, int i0, int i1, int istep) {
+                                                   const Taps<T, F> &c) {
     using fp = FP<STRICT>;
     constexpr int Q = F / 2;
     constexpr int CL = (Q - 1 + 3) / 4;          // chunks of reach; DS = 4 CL
@@ -329,7 +329,7 @@ __device__ __forceinline__ void wpt_sub_ana_chunks(const T *__restrict__ in, T *
     const int mh = m >> 1, hh = nh >> 1, ml = nh << 1;
     const int cpn = nh >> 2;
     const int sh = P2 ? (31 - __clz(cpn)) : 0, mask = cpn - 1;
-    for (int idx = i0; idx < i1; idx += istep) {
+    for (int idx = threadIdx.x; idx < (m >> 3); idx += blockDim.x) {
         int j, c0;
         if constexpr (P2) { j = idx >> sh; c0 = idx & mask; } else { j = idx / cpn; c0 = idx - j * cpn; }
         const T *E = in + j * nh, *O = E + mh;
@@ -375,15 +375,14 @@ __device__ __forceinline__ void wpt_sub_ana_chunks(const T *__restrict__ in, T *
 
 // One synthesis level of band-split sub-nodes (a_j at [j nh), d_j at m/2 + [j nh)); see wpt_sub_ana_chunks for P2.
 template <typename T, int F, bool STRICT, bool P2>
-__device__ __forceinline__ void wpt_sub_syn_chunks(const T *__restrict__ in, T *__restrict__ out, int m, int nh, const Taps<T, F> &c,
-                                                   int i0, int i1, int istep) {
+__device__ __forceinline__ void wpt_sub_syn_chunks(const T *__restrict__ in, T *__restrict__ out, int m, int nh, const Taps<T, F> &c) {
     using fp = FP<STRICT>;
     constexpr int Q = F / 2;
     constexpr int CL = (Q - 1 + 3) / 4;
     const int mh = m >> 1, ml = nh << 1;
     const int cpn = nh >> 2;
     const int sh = P2 ? (31 - __clz(cpn)) : 0, mask = cpn - 1;
-    for (int idx = i0; idx < i1; idx += istep) {
+    for (int idx = threadIdx.x; idx < (m >> 3); idx += blockDim.x) {
         int j, c0;
         if constexpr (P2) { j = idx >> sh; c0 = idx & mask; } else { j = idx / cpn; c0 = idx - j * cpn; }
         const T *A = in + j * nh, *Dd = A + mh;
@@ -510,7 +509,7 @@ __device__ __forceinline__ void leaf16_syn(const T *__restrict__ S, T *__restric
 template <typename T, int F, bool STRICT>
 __global__ void __launch_bounds__(256, 5)
 k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int levels, int64_t nodes,
-              const __grid_constant__ Taps<T, F> c, int leaf16, int wsync, const __grid_constant__ Leaf16<T> M16) {
+              const __grid_constant__ Taps<T, F> c, int leaf16, const __grid_constant__ Leaf16<T> M16) {
     using fp = FP<STRICT>;
     constexpr int Q = F / 2;
     constexpr int CL = (Q - 1 + 3) / 4;          // chunks of left / right reach
@@ -527,15 +526,8 @@ k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
     }
     __syncthreads();
     const int lv_end = leaf16 ? levels - 4 : levels;          // leaf16: the 16-sample nodes finish in one matrix stage
-    // Once a level has at least as many nodes as the CTA has warps, every warp owns whole nodes -- and a node's children live in
-    // the shared-memory ranges of the node itself -- so consecutive such levels need only a WARP barrier between them: the
-    // eight warps of a CTA drift apart instead of meeting at a block barrier per level.
-    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    auto warp_local = [&](int l) {
-        if (l < 0 || l >= lv_end || !wsync) return false;
-        const int nodes_l = 1 << l, nh = (m >> l) >> 1;
-        return nh >= 4 && (nh & 3) == 0 && nodes_l >= nwarps && (nodes_l % nwarps) == 0 && ((m >> 3) % nwarps) == 0;
-    };
+    // (Tried and measured slower, r02: warp barriers between levels whose nodes a warp owns outright -- 0.58 -> 0.69 ms per 1024
+    // signals; the block barrier per level stays.)
     for (int l = 0; l < lv_end; ++l) {
         const int ml = m >> l, nh = ml >> 1;
         const bool last = (l == levels - 1);
@@ -543,12 +535,8 @@ k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
         // child cidx (2j: approximation, 2j+1: detail) of the next level: E' at cidx*hh, O' at mh + cidx*hh
         if (nh >= 4 && (nh & 3) == 0) {
             const int cpn = nh >> 2;                          // 16-byte chunks per component of a sub-node
-            // warp-local level: the warp walks its own whole nodes (contiguous idx range), so only a warp barrier follows
-            const bool wl = warp_local(l);
-            const int per = (m >> 3) / nwarps;
-            const int i0 = wl ? warp * per + lane : (int)threadIdx.x, i1 = wl ? (warp + 1) * per : (m >> 3), istep = wl ? 32 : (int)blockDim.x;
-            if ((cpn & (cpn - 1)) == 0) wpt_sub_ana_chunks<T, F, STRICT, true>(in, out, m, nh, last, c, i0, i1, istep);
-            else wpt_sub_ana_chunks<T, F, STRICT, false>(in, out, m, nh, last, c, i0, i1, istep);
+            if ((cpn & (cpn - 1)) == 0) wpt_sub_ana_chunks<T, F, STRICT, true>(in, out, m, nh, last, c);
+            else wpt_sub_ana_chunks<T, F, STRICT, false>(in, out, m, nh, last, c);
         } else if (ml == 4) {
             for (int j = threadIdx.x; j < (m >> 2); j += blockDim.x) {
                 const T xe[2] = {in[2 * j], in[2 * j + 1]}, xo[2] = {in[mh + 2 * j], in[mh + 2 * j + 1]};
@@ -593,7 +581,7 @@ k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
                 }
             }
         }
-        if (warp_local(l) && warp_local(l + 1)) __syncwarp(); else __syncthreads();
+        __syncthreads();
         T *t = in; in = out; out = t;
     }
     if (leaf16) { leaf16_ana<T>(in, D + base, m, M16); return; }
@@ -603,7 +591,7 @@ k_wpt_sub_ana(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
 template <typename T, int F, bool STRICT>
 __global__ void __launch_bounds__(256, 5)
 k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int levels, int64_t nodes,
-              const __grid_constant__ Taps<T, F> c, int leaf16, int wsync, const __grid_constant__ Leaf16<T> M16) {
+              const __grid_constant__ Taps<T, F> c, int leaf16, const __grid_constant__ Leaf16<T> M16) {
     using fp = FP<STRICT>;
     constexpr int Q = F / 2;
     constexpr int CL = (Q - 1 + 3) / 4;
@@ -624,23 +612,13 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
     }
     __syncthreads();
     const int lv_first = leaf16 ? levels - 5 : levels - 1;
-    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // see k_wpt_sub_ana: a warp that owns whole nodes of level l wrote exactly the bands of its own nodes of level l - 1
-    auto warp_local = [&](int l) {
-        if (l < 0 || l > lv_first || !wsync) return false;
-        const int nodes_l = 1 << l, nh = (m >> l) >> 1;
-        return nh >= 4 && (nh & 3) == 0 && nodes_l >= nwarps && (nodes_l % nwarps) == 0 && ((m >> 3) % nwarps) == 0;
-    };
     for (int l = lv_first; l >= 0; --l) {
         const int ml = m >> l, nh = ml >> 1;
         // node j's output (ml samples) is band (j & 1) of its parent j >> 1 for the next, shallower level
         if (nh >= 4 && (nh & 3) == 0) {
             const int cpn = nh >> 2;
-            const bool own = warp_local(l);
-            const int per = (m >> 3) / nwarps;
-            const int i0 = own ? warp * per + lane : (int)threadIdx.x, i1 = own ? (warp + 1) * per : (m >> 3), istep = own ? 32 : (int)blockDim.x;
-            if ((cpn & (cpn - 1)) == 0) wpt_sub_syn_chunks<T, F, STRICT, true>(in, out, m, nh, c, i0, i1, istep);
-            else wpt_sub_syn_chunks<T, F, STRICT, false>(in, out, m, nh, c, i0, i1, istep);
+            if ((cpn & (cpn - 1)) == 0) wpt_sub_syn_chunks<T, F, STRICT, true>(in, out, m, nh, c);
+            else wpt_sub_syn_chunks<T, F, STRICT, false>(in, out, m, nh, c);
         } else if (ml == 4) {
             for (int j = threadIdx.x; j < (m >> 2); j += blockDim.x) {
                 const T a[2] = {in[2 * j], in[2 * j + 1]}, d[2] = {in[mh + 2 * j], in[mh + 2 * j + 1]};
@@ -683,7 +661,7 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
                 o[2 * u + 1] = fp::add(rao, rdo);
             }
         }
-        if (warp_local(l) && warp_local(l - 1)) __syncwarp(); else __syncthreads();
+        __syncthreads();
         T *t = in; in = out; out = t;
     }
     for (int i = threadIdx.x; i < m; i += blockDim.x) D[base + i] = in[i];
@@ -750,19 +728,18 @@ static int wpt_sub_F(const T *S, T *D, int64_t n, int m, int levels, int64_t nod
     // fast mode, full-depth tree, 16-byte granular rows: the last four levels as one 16 x 16 map per node
     const bool leaf16 = !STRICT && levels >= 4 && ((int64_t)m >> levels) == 1 && (m >> 4) <= nthr && env_int_fp("WB200_WPT_LEAF16", 1) != 0 &&
                         ((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(D)) & 15) == 0 && ((n * (int64_t)sizeof(T)) % 16) == 0;
-    const int wsync = env_int_fp("WB200_WPT_WARPSYNC", 1) != 0 ? 1 : 0;      // warp barriers between warp-local levels
     Leaf16<T> MA, MS;
     if (leaf16) leaf16_matrices<T>(fc, MA, MS); else { std::memset(&MA, 0, sizeof(MA)); std::memset(&MS, 0, sizeof(MS)); }
     if (fw) {
         auto kern = k_wpt_sub_ana<T, F, STRICT>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
         LaunchScope scope("wpt_subtree_analysis", st);
-        kern<<<(unsigned)nblk, nthr, smem, st>>>(S, D, n, m, levels, nodes, taps, leaf16 ? 1 : 0, wsync, MA);
+        kern<<<(unsigned)nblk, nthr, smem, st>>>(S, D, n, m, levels, nodes, taps, leaf16 ? 1 : 0, MA);
     } else {
         auto kern = k_wpt_sub_syn<T, F, STRICT>;
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
         LaunchScope scope("wpt_subtree_synthesis", st);
-        kern<<<(unsigned)nblk, nthr, smem, st>>>(S, D, n, m, levels, nodes, taps, leaf16 ? 1 : 0, wsync, MS);
+        kern<<<(unsigned)nblk, nthr, smem, st>>>(S, D, n, m, levels, nodes, taps, leaf16 ? 1 : 0, MS);
     }
     return check_launch("wpt_subtree") ? 1 : -1;
 }

@@ -121,25 +121,28 @@ k_pkt_ana(const T *__restrict__ src, T *__restrict__ dst, int64_t n, int64_t nj,
     // last level: bands 2bb, 2bb+1 of level K go to HBM, each rotated by its accumulated detail shift
     {
         const int nb = 1 << (K - 1), cnt = pl.NA[K] / PA, Sp = pl.S[K - 1];
-        const int64_t lenK = nj >> K, sK = s >> K;
+        const int lenK = (int)(nj >> K), sK = (int)(s >> K);      // 32-bit band arithmetic (nj <= 2^30); shifts are < lenK: one conditional wrap each
         int bb = threadIdx.x / cnt, it = threadIdx.x - bb * cnt;
         while (bb < nb) {
             int op = 0;                                   // offset of the parent band bb (level K-1): sum of its detail bits' shifts
             for (int i = K - 2; i >= 0; --i) op = (op >> 1) + (((bb >> i) & 1) ? G::DS : 0);
             // children: o = op/2 (approximation), op/2 + DS (detail); band beta lives at onode + beta*lenK, sample index mod lenK
-            const int64_t sa = (sK + (op >> 1)) % lenK, sd = (sK + (op >> 1) + G::DS) % lenK;
+            int sa = sK + (op >> 1);
+            if (sa >= lenK) sa -= lenK;
+            int sd = sa + G::DS;
+            if (sd >= lenK) sd -= lenK;
             T *pa = onode + (int64_t)(2 * bb) * lenK, *pd = pa + lenK;
             const bool vec = PA == 1 || (((sa | sd) & 1) == 0);   // even starts: the pair stores stay 8-byte aligned and never straddle the wrap
             const int p = PA * it;
             T a[PA], d[PA];
             pkt_pairs<T, F, STRICT, PA>(in + bb * Sp + 2 * p, c, a, d);
-            int64_t ia = sa + p, id = sd + p;
+            int ia = sa + p, id = sd + p;
             if (ia >= lenK) ia -= lenK;
             if (id >= lenK) id -= lenK;
             if constexpr (PA == 2) {
                 if (vec) { gstore2(pa + ia, a[0], a[1]); gstore2(pd + id, d[0], d[1]); }
                 else {
-                    const int64_t ia1 = ia + 1 >= lenK ? ia + 1 - lenK : ia + 1, id1 = id + 1 >= lenK ? id + 1 - lenK : id + 1;
+                    const int ia1 = ia + 1 >= lenK ? ia + 1 - lenK : ia + 1, id1 = id + 1 >= lenK ? id + 1 - lenK : id + 1;
                     __stcs(pa + ia, a[0]); __stcs(pa + ia1, a[1]);
                     __stcs(pd + id, d[0]); __stcs(pd + id1, d[1]);
                 }
@@ -300,7 +303,7 @@ static int wpt_fused_F(const T *S, T *D, int64_t n, int64_t nj, int K, int64_t n
     const int64_t ntiles = nj / tile;
     const int64_t nblk = ntiles * nodes * B;
     if (nblk > 0x7fffffffLL || nblk <= 0) return 0;
-    const int nthr = env_int_pk("WB200_WPTFUSED_NT", 256) & ~31;
+    const int nthr = env_int_pk("WB200_WPTFUSED_NT", 128) & ~31;
     if (fw) {
         PktAnaPlan pl;
         std::memset(&pl, 0, sizeof(pl));
