@@ -60,7 +60,8 @@ def main():
     print("\n## `-Xptxas -v` resource lines (wavelets.jl_b200/lib/obj/*.ptxas.log), headline instantiations\n")
     want = [r"k_ana_tiles<float, 8, false>", r"k_syn_tiles<float, 8, false>", r"k_ana_tiles<double, 8, false>", r"k_syn_tiles<double, 8, false>",
             r"k_lift1d_(ana|syn)<float, wb::ShapeCdf97\w, false", r"k_lift2d_fwd_tma<float, wb::ShapeCdf97F, false", r"k_lift2d_inv_tma<float, wb::ShapeCdf97I, false",
-            r"k_lift2d_fwd_tma<float, wb::ShapeFirA<8>, false", r"k_fir3d_\w+<float, 12, false", r"k_lift2d_tailfast<float, wb::ShapeCdf97F, false", r"k_wpt_sub_ana<float, 16, false", r"k_wpt_sub_syn<float, 16, false"]
+            r"k_lift2d_fwd_tma<float, wb::ShapeFirA<8>, false", r"k_fir3d_\w+<float, 12, false", r"k_lift2d_tailfast<float, wb::ShapeCdf97F, false", r"k_wpt_sub_ana<float, 16, false", r"k_wpt_sub_syn<float, 16, false",
+            r"k_pkt_ana<float, 16, false", r"k_pkt_syn<float, 16, false"]
     print("| kernel | registers | spill stores / loads | static smem |")
     print("|---|---|---|---|")
     for log in sorted(glob.glob(os.path.join(ROOT, "wavelets.jl_b200", "lib", "obj", "*.ptxas.log"))):

@@ -34,7 +34,7 @@ template <typename T, int F, bool STRICT>
 __global__ void __launch_bounds__(512)
 k_ana_tiles(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, int64_t n0, int lvl0,
             T *__restrict__ dst_a, int64_t dst_a_stride,
-            const __grid_constant__ Taps<T, F> c, const __grid_constant__ AnaPlan pl) {
+            const __grid_constant__ Taps<T, F> c, const __grid_constant__ AnaPlan pl, int pf) {
     constexpr int PA = AnaPairs<T>::value;
     using G = FGeom<F, PA>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -54,6 +54,21 @@ k_ana_tiles(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, in
         tma_load_wrapped<T>(bufA, xc, s, count, ncur, bar);
     }
     __syncthreads();       // barrier initialised before anyone polls it
+    // Software prefetch into L2 of the tile a CTA `pf` launches further on will stage (CTAs start in linear block order), issued
+    // in the shadow of this CTA's own TMA wait.  With ~8 small CTAs per SM only the ones still waiting for their tile have loads
+    // in flight (27 % of the warp samples of profiles/r02h_fused1d_f32.md sit in that wait with DRAM at 78 %); the prefetch keeps
+    // DRAM busy on their behalf and turns the later TMA load into an L2 hit.
+    if (pf > 0 && threadIdx.x == 0) {
+        const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x + (unsigned)pf;      // (grid sizes are checked to fit 31 bits)
+        const unsigned pcol = lin / gridDim.x;
+        if (pcol < gridDim.y) {
+            const int64_t ps = (int64_t)(lin - pcol * gridDim.x) * pl.tile;
+            const int64_t room = ncur - ps;
+            const int count = pl.tile + pl.h0;
+            const int64_t cnt = room < (int64_t)count ? room : (int64_t)count;
+            tma_prefetch_l2(src + (int64_t)pcol * src_stride + ps, (uint32_t)(cnt * sizeof(T)));
+        }
+    }
     mbar_wait(bar, 0);
 
     const T *in = bufA;
@@ -184,7 +199,7 @@ __global__ void __launch_bounds__(512)
 k_syn_tiles(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restrict__ x, int64_t n0, int lvl0,
             T *__restrict__ dst, int64_t dst_stride,
             const __grid_constant__ Taps<T, F> c, const __grid_constant__ SynPlan pl,
-            const __grid_constant__ ThreshEpi epi, int thr_a) {
+            const __grid_constant__ ThreshEpi epi, int thr_a, int pf) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     T *sm = reinterpret_cast<T *>(smem_raw + 128);
@@ -208,6 +223,27 @@ k_syn_tiles(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restrict
         }
     }
     __syncthreads();
+    // L2 prefetch for the CTA `pf` launches further on (see k_ana_tiles), in the shadow of this CTA's own TMA waits.  The slices
+    // of the coarse levels are small (1 KB at level 4 of a 4096-sample tile), so level l is prefetched by every 2^(l-1)-th tile
+    // for 2^(l-1) tiles at once: about two 8 KB prefetch operations per CTA instead of five small ones.
+    if (pf > 0 && threadIdx.x == 0) {
+        const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x + (unsigned)pf;
+        const unsigned pcol = lin / gridDim.x;
+        if (pcol < gridDim.y) {
+            const unsigned pt = lin - pcol * gridDim.x;                 // tile index inside the column
+            const T *pxc = x + (int64_t)pcol * n0;
+            for (int l = 1; l <= K; ++l) {
+                const unsigned grp = 1u << ((l - 1) < 3 ? (l - 1) : 3);
+                if (pt & (grp - 1)) continue;
+                const int64_t len = ncur >> l;
+                const int64_t lo = ((int64_t)pt * pl.tile) >> l;
+                int64_t hi = lo + (int64_t)grp * (pl.tile >> l);
+                if (hi > len) hi = len;
+                if (hi > lo) tma_prefetch_l2(pxc + (n0 >> (lvl0 + l)) + lo, (uint32_t)((hi - lo) * sizeof(T)));
+                if (l == K && hi > lo) tma_prefetch_l2(asrc + (int64_t)pcol * asrc_stride + lo, (uint32_t)((hi - lo) * sizeof(T)));
+            }
+        }
+    }
 
     const T *abuf = sm + pl.aoff;
     const double tthr = epi.kind >= 0 ? (epi.sigma_dev ? __dmul_rn(*epi.sigma_dev, epi.tfac) : epi.t_host) : 0.0;
@@ -410,6 +446,14 @@ template <typename T> static int tile_max(bool fw) {
 }
 constexpr int KMAX_DEFAULT = 4;
 
+// L2 prefetch distance of the tile kernels in CTAs (WB200_F1D_PREFETCH / WB200_F1D_PREFETCH_INV; 0 = off).  Interleaved A/B
+// (tools/ab_prefetch.py, profiles/r02h_prefetch_ab.md): the FORWARD kernel -- one contiguous read stream per column -- gains
+// 4-9 % with 600-1200 CTAs of lookahead (about one resident generation: 148 SMs x 6-8 CTAs); the INVERSE kernel, which reads
+// five streams at power-of-two offsets, loses 7-13 % at every distance, so its default stays off.
+static int tile_prefetch(bool fw) {
+    const int v = fw ? env_int("WB200_F1D_PREFETCH", 888) : env_int("WB200_F1D_PREFETCH_INV", 0);
+    return v < 0 ? 0 : v;
+}
 // threads per tile CTA (WB200_F1D_NT / WB200_F1D_NT_INV)
 static int tile_threads(bool fw) {
     const int v = env_int(fw ? "WB200_F1D_NT" : "WB200_F1D_NT_INV", 96);
@@ -580,7 +624,8 @@ static int32_t run_fused_1d(const PassOp<T> &op, T *y, const T *x, int64_t n, in
             dim3 grid((unsigned)(ncur / sg.tile), (unsigned)B);
             {
                 LaunchScope scope("fused_ana_tiles", st);
-                kern<<<grid, tile_threads(true), smem, st>>>(src, sstride, y, n, sg.lv0, dsta, dstride, taps, pl);
+                const int pfv = ((uint64_t)grid.x * grid.y + (uint64_t)tile_prefetch(true) < 0x7fffffffULL) ? tile_prefetch(true) : 0;
+                kern<<<grid, tile_threads(true), smem, st>>>(src, sstride, y, n, sg.lv0, dsta, dstride, taps, pl, pfv);
             }
             if (!check_launch("fused_ana_tiles")) { rc = WB200_ECUDA; return finish(); }
         }
@@ -632,7 +677,8 @@ static int32_t run_fused_1d(const PassOp<T> &op, T *y, const T *x, int64_t n, in
             dim3 grid((unsigned)(ncur / sg.tile), (unsigned)B);
             {
                 LaunchScope scope("fused_syn_tiles", st);
-                kern<<<grid, tile_threads(false), smem, st>>>(asrc, astride, x, n, sg.lv0, dst, dstride, taps, pl, op.epi, last_overall ? 1 : 0);
+                const int pfv = ((uint64_t)grid.x * grid.y + (uint64_t)tile_prefetch(false) < 0x7fffffffULL) ? tile_prefetch(false) : 0;
+                kern<<<grid, tile_threads(false), smem, st>>>(asrc, astride, x, n, sg.lv0, dst, dstride, taps, pl, op.epi, last_overall ? 1 : 0, pfv);
             }
             if (!check_launch("fused_syn_tiles")) { rc = WB200_ECUDA; return finish(); }
         }

@@ -31,6 +31,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src, ui
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// L2 prefetch of a contiguous global range (16-byte aligned, size a multiple of 16): no shared-memory destination, no barrier
+__device__ __forceinline__ void tma_prefetch_l2(const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // Copy `count` elements of the periodic line `line` (period n) starting at (possibly negative / overflowing)
 // index `lo` into dst.  lo, count and n are multiples of the 16-byte vector, count <= n.  Returns bytes issued.
 template <typename T>

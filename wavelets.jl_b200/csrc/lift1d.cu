@@ -92,7 +92,7 @@ template <typename T, class S, bool STRICT>
 __global__ void __launch_bounds__(512)
 k_lift1d_ana(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, int64_t n0, int lvl0,
              T *__restrict__ dst_a, int64_t dst_a_stride, const __grid_constant__ LiftCoefs<T> lc,
-             const __grid_constant__ AnaPlanL pl) {
+             const __grid_constant__ AnaPlanL pl, int pf) {
     using fp = FP<STRICT>;
     constexpr int SEG = Geo<T>::SEG_A, G = Geo<T>::G;
     constexpr int HM = HaloE<S>::value, NP = SEG + 2 * HM;
@@ -114,6 +114,12 @@ k_lift1d_ana(const T *__restrict__ src, int64_t src_stride, T *__restrict__ y, i
         tma_load_wrapped<T>(bufA, xc, s - pl.E[0], count, ncur, bar);
     }
     __syncthreads();
+    if (pf > 0 && threadIdx.x == 0) {      // L2 prefetch of the tile the CTA `pf` launches further on will stage (fused1d.cu: k_ana_tiles)
+        const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x + (unsigned)pf;
+        const unsigned pcol = lin / gridDim.x;
+        if (pcol < gridDim.y)
+            tma_prefetch_l2(src + (int64_t)pcol * src_stride + (int64_t)(lin - pcol * gridDim.x) * pl.tile, (uint32_t)(pl.tile * sizeof(T)));
+    }
     mbar_wait(bar, 0);
 
     // per-warp staging of the detail outputs: a lane's segment is SEG consecutive coefficients, so direct stores would touch
@@ -185,7 +191,7 @@ template <typename T, class S, bool STRICT>
 __global__ void __launch_bounds__(512)
 k_lift1d_syn(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restrict__ x, int64_t n0, int lvl0,
              T *__restrict__ dst, int64_t dst_stride, const __grid_constant__ LiftCoefs<T> lc,
-             const __grid_constant__ SynPlanL pl) {
+             const __grid_constant__ SynPlanL pl, int pf) {
     using fp = FP<STRICT>;
     constexpr int SEG = Geo<T>::SEG_S, V = Geo<T>::V;
     constexpr int HM = HaloE<S>::value, NP = SEG + 2 * HM, NW = SEG + 8;
@@ -212,6 +218,24 @@ k_lift1d_syn(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restric
         }
     }
     __syncthreads();
+    if (pf > 0 && threadIdx.x == 0) {      // L2 prefetch for the CTA `pf` launches further on; level l by every 2^(l-1)-th tile (fused1d.cu: k_syn_tiles)
+        const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x + (unsigned)pf;
+        const unsigned pcol = lin / gridDim.x;
+        if (pcol < gridDim.y) {
+            const unsigned pt = lin - pcol * gridDim.x;
+            const T *pxc = x + (int64_t)pcol * n0;
+            for (int l = 1; l <= K; ++l) {
+                const unsigned grp = 1u << ((l - 1) < 3 ? (l - 1) : 3);
+                if (pt & (grp - 1)) continue;
+                const int64_t len = ncur >> l;
+                const int64_t lo = ((int64_t)pt * pl.tile) >> l;
+                int64_t hi = lo + (int64_t)grp * (pl.tile >> l);
+                if (hi > len) hi = len;
+                if (hi > lo) tma_prefetch_l2(pxc + (n0 >> (lvl0 + l)) + lo, (uint32_t)((hi - lo) * sizeof(T)));
+                if (l == K && hi > lo) tma_prefetch_l2(asrc + (int64_t)pcol * asrc_stride + lo, (uint32_t)((hi - lo) * sizeof(T)));
+            }
+        }
+    }
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T *wst = sm + (pl.woff >= 0 ? pl.woff : 0) + warp * (32 * 2 * SEG);
@@ -418,6 +442,14 @@ template <typename T> static PlanL plan_l(int64_t n, int L, int HM, bool fw) {
     p.ok = true;
     return p;
 }
+// L2 prefetch distance of the tile kernels in CTAs (WB200_LIFT1D_PREFETCH / WB200_LIFT1D_PREFETCH_INV; 0 = off), dropped when the grid
+// does not fit 31 bits.  Same outcome as for the filter kernels (profiles/r02h_prefetch_ab.md): forward +7 % at ~900 CTAs ahead,
+// inverse -14 % at every distance, so only the forward kernel prefetches by default.
+static int lift_prefetch(bool fw, dim3 grid) {
+    int v = fw ? env_l("WB200_LIFT1D_PREFETCH", 888) : env_l("WB200_LIFT1D_PREFETCH_INV", 0);
+    if (v < 0 || (uint64_t)grid.x * grid.y + (uint64_t)v >= 0x7fffffffULL) v = 0;
+    return v;
+}
 // threads per CTA: the level-1 segment count of a tile spread over whole rounds (a 256-thread CTA left a third of its lanes
 // idle on the 342 level-1 segments of an 8192-sample synthesis tile)
 static int block_for(int segments, const char *envname) {
@@ -563,7 +595,7 @@ static int32_t run_l1(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t 
             dim3 grid((unsigned)(ncur / sg.tile), (unsigned)B);
             {
                 LaunchScope scope("fused_lift1d_ana", st);
-                kern<<<grid, nt, smem, st>>>(src, sstride, y, n, sg.lv0, dsta, dstride, lc, pl);
+                kern<<<grid, nt, smem, st>>>(src, sstride, y, n, sg.lv0, dsta, dstride, lc, pl, lift_prefetch(true, grid));
             }
             if (!check_launch("fused_lift1d_ana")) return WB200_ECUDA;
         }
@@ -615,7 +647,7 @@ static int32_t run_l1(const PassOp<T> &op, T *y, const T *x, int64_t n, int64_t 
         dim3 grid((unsigned)(ncur / sg.tile), (unsigned)B);
         {
             LaunchScope scope("fused_lift1d_syn", st);
-            kern<<<grid, nt, smem, st>>>(asrc, astride, x, n, sg.lv0, dst, dstride, lc, pl);
+            kern<<<grid, nt, smem, st>>>(asrc, astride, x, n, sg.lv0, dst, dstride, lc, pl, lift_prefetch(false, grid));
         }
         if (!check_launch("fused_lift1d_syn")) return WB200_ECUDA;
     }
