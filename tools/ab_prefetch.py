@@ -13,8 +13,9 @@ x = torch.randn((B, 1 << 20), device="cuda", dtype=torch.float64 if f64 else tor
 y = wb.dwtc(x, wl)
 gb = 2 * x.element_size() * B * (1 << 20) / 1e9
 KEYS = ["WB200_LIFT1D_PREFETCH", "WB200_LIFT1D_PREFETCH_INV"] if lift else ["WB200_F1D_PREFETCH", "WB200_F1D_PREFETCH_INV"]
-dists = [0, 296, 592, 888, 1184, 1480, 1776]
-def timeit(fn, reps=5):
+dists = [int(v) for v in os.environ.get("AB_DISTS", "0,296,592,888,1184,1480,1776").split(",")]
+REPS = int(os.environ.get("AB_REPS", "5"))      # AB_REPS=12 with 8192 columns: long enough to sit at the power cap
+def timeit(fn, reps=REPS):
     fn(); fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()

@@ -171,8 +171,9 @@ __device__ __forceinline__ void ana_level(const T *__restrict__ in, int NA, int 
     const int step = PA * blockDim.x;
     int p = PA * threadIdx.x;
     const int e1 = wrap_at < ND ? wrap_at : ND;
+    const int nseg = wrap_at < ND ? 2 : 1;        // only the last tile of a line has a second (wrapped) detail segment
 #pragma unroll 1
-    for (int seg = 0; seg < 2; ++seg) {
+    for (int seg = 0; seg < nseg; ++seg) {
         T *__restrict__ dp = (seg ? d1 : d0) + p;      // running detail pointer: one 64-bit add per iteration
         const int e = seg ? ND : e1;
         for (; p < e; p += step, dp += step) {
