@@ -167,3 +167,22 @@ def test_threshold_module_host_side():
                lambda: wb.bestbasistree(torch.randn(8), wavelet(WT.db2)), lambda: wb.modwt(torch.randn(8), wavelet(WT.db2))):
         with pytest.raises(TypeError, match="no CPU path"):
             fn()
+
+
+def test_fused_packet_level_index_arithmetic():
+    """tools/wptfused_emul.py: the plans, band offsets, rotated stores and staged ranges of the fused K-level packet kernels
+    (wptfused.cu) emulated in numpy against a direct periodic packet transform -- a CPU dry run of the index arithmetic the GPU
+    tests then check bit for bit"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("wptfused_emul", os.path.join(ROOT, "tools", "wptfused_emul.py"))
+    em = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(em)
+    for F, K, tile, nj, PA, vec in [(16, 4, 256, 1024, 2, 4), (8, 3, 256, 1024, 2, 4), (18, 4, 256, 1024, 1, 2), (12, 2, 256, 768, 2, 4)]:
+        h, g = em.qmf_pair(F)
+        x = em.rng.standard_normal(nj)
+        ref = em.wpt_ref(x, h, g, K)
+        assert np.max(np.abs(ref - em.emul_ana(x, h, g, K, tile, PA, vec))) < 1e-9
+        cur = np.split(ref, 1 << K)
+        for _ in range(K):
+            cur = [em.syn_ref(cur[2 * i], cur[2 * i + 1], h, g) for i in range(len(cur) // 2)]
+        assert np.max(np.abs(cur[0] - em.emul_syn(ref, h, g, K, tile))) < 1e-9

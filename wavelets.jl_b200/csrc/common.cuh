@@ -16,7 +16,10 @@ constexpr int MAXCOEF = WB200_MAX_LIFT_COEF;
 //   STRICT = true : every product and every sum is rounded separately (__fmul_rn/__fadd_rn are never
 //                   contracted by nvcc), in the reference's operation order -> bit-identical to the
 //                   Julia CPU path (which never fuses a*b+c).
-//   STRICT = false: same order, a*b+c contracted to one FMA (one rounding less per tap).
+//   STRICT = false: same order, a*b+c contracted to one FMA (one rounding less per tap).  One more liberty in the
+//                   synthesis kernels: the reference adds the approximation-band sum and the detail-band sum of an output
+//                   last; fast mode lets the detail terms continue the approximation's accumulator (one chain: no second
+//                   FMUL, no final FADD -- 32 instead of 36 floating-point instructions per two db4 output pairs).
 // ---------------------------------------------------------------------------------------------------
 template <bool STRICT> struct FP {
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }

@@ -205,15 +205,16 @@ k_walk_syn(View<const T> slo, View<const T> shi, View<const T> salt, int64_t thr
                 rae = fp::mac(rae, c.h[2 * j], wa[k + Q - 1 - j]);
                 rao = fp::mac(rao, c.h[2 * j + 1], wa[k + Q - 1 - j]);
             }
-            T rde = fp::mul(c.g[1], wd[k]);
-            T rdo = fp::mul(c.g[0], wd[k]);
+            T rde, rdo;      // fast mode: the detail terms continue the approximation's chain (no second FMUL, no final FADD)
+            if constexpr (STRICT) { rde = fp::mul(c.g[1], wd[k]); rdo = fp::mul(c.g[0], wd[k]); }
+            else { rde = fp::mac(rae, c.g[1], wd[k]); rdo = fp::mac(rao, c.g[0], wd[k]); }
 #pragma unroll
             for (int j = 1; j < Q; ++j) {
                 rde = fp::mac(rde, c.g[2 * j + 1], wd[k + j]);
                 rdo = fp::mac(rdo, c.g[2 * j], wd[k + j]);
             }
-            o[(2 * (u0 + k)) * dst.ls] = fp::add(rae, rde);
-            o[(2 * (u0 + k) + 1) * dst.ls] = fp::add(rao, rdo);
+            o[(2 * (u0 + k)) * dst.ls] = (STRICT ? fp::add(rae, rde) : rde);
+            o[(2 * (u0 + k) + 1) * dst.ls] = (STRICT ? fp::add(rao, rdo) : rdo);
         }
     }
 }
@@ -299,15 +300,16 @@ __device__ __forceinline__ void tiny_syn(const T (&a)[NH], const T (&d)[NH], T (
             rae = fp::mac(rae, c.h[2 * t], a[(u - t + BIG) % NH]);
             rao = fp::mac(rao, c.h[2 * t + 1], a[(u - t + BIG) % NH]);
         }
-        T rde = fp::mul(c.g[1], d[u % NH]);
-        T rdo = fp::mul(c.g[0], d[u % NH]);
+        T rde, rdo;      // fast mode: the detail terms continue the approximation's chain (no second FMUL, no final FADD)
+        if constexpr (STRICT) { rde = fp::mul(c.g[1], d[u % NH]); rdo = fp::mul(c.g[0], d[u % NH]); }
+        else { rde = fp::mac(rae, c.g[1], d[u % NH]); rdo = fp::mac(rao, c.g[0], d[u % NH]); }
 #pragma unroll
         for (int t = 1; t < Q; ++t) {
             rde = fp::mac(rde, c.g[2 * t + 1], d[(u + t) % NH]);
             rdo = fp::mac(rdo, c.g[2 * t], d[(u + t) % NH]);
         }
-        x[2 * u] = fp::add(rae, rde);
-        x[2 * u + 1] = fp::add(rao, rdo);
+        x[2 * u] = (STRICT ? fp::add(rae, rde) : rde);
+        x[2 * u + 1] = (STRICT ? fp::add(rao, rdo) : rdo);
     }
 }
 
@@ -416,15 +418,16 @@ __device__ __forceinline__ void wpt_sub_syn_chunks(const T *__restrict__ in, T *
                 rae = fp::mac(rae, c.h[2 * t], wa[4 * CL + r - t]);
                 rao = fp::mac(rao, c.h[2 * t + 1], wa[4 * CL + r - t]);
             }
-            T rde = fp::mul(c.g[1], wd[r]);
-            T rdo = fp::mul(c.g[0], wd[r]);
+            T rde, rdo;      // fast mode: the detail terms continue the approximation's chain (no second FMUL, no final FADD)
+            if constexpr (STRICT) { rde = fp::mul(c.g[1], wd[r]); rdo = fp::mul(c.g[0], wd[r]); }
+            else { rde = fp::mac(rae, c.g[1], wd[r]); rdo = fp::mac(rao, c.g[0], wd[r]); }
 #pragma unroll
             for (int t = 1; t < Q; ++t) {
                 rde = fp::mac(rde, c.g[2 * t + 1], wd[r + t]);
                 rdo = fp::mac(rdo, c.g[2 * t], wd[r + t]);
             }
-            xo[2 * r] = fp::add(rae, rde);
-            xo[2 * r + 1] = fp::add(rao, rdo);
+            xo[2 * r] = (STRICT ? fp::add(rae, rde) : rde);
+            xo[2 * r + 1] = (STRICT ? fp::add(rao, rdo) : rdo);
         }
         T *o = out + (j & 1) * mh + (j >> 1) * ml + 8 * c0;
         st4(o, xo[0], xo[1], xo[2], xo[3]);
@@ -648,8 +651,9 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
                     rao = fp::mac(rao, c.h[2 * t + 1], a[ia]);
                 }
                 int id = u;
-                T rde = fp::mul(c.g[1], d[id]);
-                T rdo = fp::mul(c.g[0], d[id]);
+                T rde, rdo;      // fast mode: the detail terms continue the approximation's chain (no second FMUL, no final FADD)
+                if constexpr (STRICT) { rde = fp::mul(c.g[1], d[id]); rdo = fp::mul(c.g[0], d[id]); }
+                else { rde = fp::mac(rae, c.g[1], d[id]); rdo = fp::mac(rao, c.g[0], d[id]); }
 #pragma unroll
                 for (int t = 1; t < Q; ++t) {
                     if (++id == nh) id = 0;
@@ -657,8 +661,8 @@ k_wpt_sub_syn(const T *__restrict__ S, T *__restrict__ D, int64_t n, int m, int 
                     rdo = fp::mac(rdo, c.g[2 * t], d[id]);
                 }
                 T *o = out + (j & 1) * mh + (j >> 1) * ml;
-                o[2 * u] = fp::add(rae, rde);
-                o[2 * u + 1] = fp::add(rao, rdo);
+                o[2 * u] = (STRICT ? fp::add(rae, rde) : rde);
+                o[2 * u + 1] = (STRICT ? fp::add(rao, rdo) : rdo);
             }
         }
         __syncthreads();

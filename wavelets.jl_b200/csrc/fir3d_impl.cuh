@@ -401,14 +401,15 @@ k_fir3d_inv(const T *__restrict__ ll, int64_t ld_ll, int64_t ps_ll, int64_t bs_l
                                 rae = fp::mac(rae, fc.h[2 * k], a2[pr + H - k]);
                                 rao = fp::mac(rao, fc.h[2 * k + 1], a2[pr + H - k]);
                             }
-                            T rde = fp::mul(fc.g[1], d2[pr]);
-                            T rdo = fp::mul(fc.g[0], d2[pr]);
+                            T rde, rdo;      // fast mode: the detail terms continue the approximation's chain (no second FMUL, no final FADD)
+                            if constexpr (STRICT) { rde = fp::mul(fc.g[1], d2[pr]); rdo = fp::mul(fc.g[0], d2[pr]); }
+                            else { rde = fp::mac(rae, fc.g[1], d2[pr]); rdo = fp::mac(rao, fc.g[0], d2[pr]); }
 #pragma unroll
                             for (int k = 1; k < Q; ++k) {
                                 rde = fp::mac(rde, fc.g[2 * k + 1], d2[pr + k]);
                                 rdo = fp::mac(rdo, fc.g[2 * k], d2[pr + k]);
                             }
-                            const T x0 = fp::add(rae, rde), x1 = fp::add(rao, rdo);
+                            const T x0 = (STRICT ? fp::add(rae, rde) : rde), x1 = (STRICT ? fp::add(rao, rdo) : rdo);
                             if (pl == 0) { ringA[2 * pr][ph % Q] = x0; ringA[2 * pr + 1][ph % Q] = x1; }
                             else         { ringD[2 * pr][ph % Q] = x0; ringD[2 * pr + 1][ph % Q] = x1; }
                         }
@@ -426,16 +427,17 @@ k_fir3d_inv(const T *__restrict__ ll, int64_t ld_ll, int64_t ps_ll, int64_t bs_l
                                 rae = fp::mac(rae, fc.h[2 * k], ringA[pos][(ph - k + Q) % Q]);
                                 rao = fp::mac(rao, fc.h[2 * k + 1], ringA[pos][(ph - k + Q) % Q]);
                             }
-                            T rde = fp::mul(fc.g[1], ringD[pos][(ph + 1) % Q]);
-                            T rdo = fp::mul(fc.g[0], ringD[pos][(ph + 1) % Q]);
+                            T rde, rdo;      // fast mode: the detail terms continue the approximation's chain (no second FMUL, no final FADD)
+                            if constexpr (STRICT) { rde = fp::mul(fc.g[1], ringD[pos][(ph + 1) % Q]); rdo = fp::mul(fc.g[0], ringD[pos][(ph + 1) % Q]); }
+                            else { rde = fp::mac(rae, fc.g[1], ringD[pos][(ph + 1) % Q]); rdo = fp::mac(rao, fc.g[0], ringD[pos][(ph + 1) % Q]); }
 #pragma unroll
                             for (int k = 1; k < Q; ++k) {
                                 rde = fp::mac(rde, fc.g[2 * k + 1], ringD[pos][(ph + k + 1) % Q]);
                                 rdo = fp::mac(rdo, fc.g[2 * k], ringD[pos][(ph + k + 1) % Q]);
                             }
                             T *po = pw + (int64_t)pos * ld_d;
-                            po[0] = fp::add(rae, rde);
-                            po[ps_d] = fp::add(rao, rdo);
+                            po[0] = (STRICT ? fp::add(rae, rde) : rde);
+                            po[ps_d] = (STRICT ? fp::add(rao, rdo) : rdo);
                         }
                     }
                 }

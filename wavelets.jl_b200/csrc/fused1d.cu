@@ -385,15 +385,16 @@ k_syn_tail(const T *__restrict__ x, int64_t n, T *__restrict__ dst, int64_t dst_
                     rao = fp::mac(rao, c.h[2 * k + 1], a[QAP + ia]);
                 }
                 int id = u;
-                T rde = fp::mul(c.g[1], d[id]);
-                T rdo = fp::mul(c.g[0], d[id]);
+                T rde, rdo;      // fast mode: the detail terms continue the approximation's chain (no second FMUL, no final FADD)
+                if constexpr (STRICT) { rde = fp::mul(c.g[1], d[id]); rdo = fp::mul(c.g[0], d[id]); }
+                else { rde = fp::mac(rae, c.g[1], d[id]); rdo = fp::mac(rao, c.g[0], d[id]); }
 #pragma unroll
                 for (int k = 1; k < Q; ++k) {
                     if (++id == nh) id = 0;
                     rde = fp::mac(rde, c.g[2 * k + 1], d[id]);
                     rdo = fp::mac(rdo, c.g[2 * k], d[id]);
                 }
-                const T x0 = fp::add(rae, rde), x1 = fp::add(rao, rdo);
+                const T x0 = (STRICT ? fp::add(rae, rde) : rde), x1 = (STRICT ? fp::add(rao, rdo) : rdo);
                 if (last) { dc[2 * u] = x0; dc[2 * u + 1] = x1; }
                 else      { out[QAP + 2 * u] = x0; out[QAP + 2 * u + 1] = x1; }
             }

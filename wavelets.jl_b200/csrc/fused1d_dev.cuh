@@ -253,15 +253,16 @@ __device__ __forceinline__ void syn_quad(const T *__restrict__ pa, const T *__re
             rae = fp::mac(rae, c.h[2 * k], wa[Q4 + r - k]);
             rao = fp::mac(rao, c.h[2 * k + 1], wa[Q4 + r - k]);
         }
-        T rde = fp::mul(c.g[1], wd[r]);
-        T rdo = fp::mul(c.g[0], wd[r]);
+        T rde, rdo;      // fast mode: the detail terms continue the approximation's chain (no second FMUL, no final FADD)
+        if constexpr (STRICT) { rde = fp::mul(c.g[1], wd[r]); rdo = fp::mul(c.g[0], wd[r]); }
+        else { rde = fp::mac(rae, c.g[1], wd[r]); rdo = fp::mac(rao, c.g[0], wd[r]); }
 #pragma unroll
         for (int k = 1; k < Q; ++k) {
             rde = fp::mac(rde, c.g[2 * k + 1], wd[r + k]);
             rdo = fp::mac(rdo, c.g[2 * k], wd[r + k]);
         }
-        o[2 * r] = fp::add(rae, rde);
-        o[2 * r + 1] = fp::add(rao, rdo);
+        o[2 * r] = (STRICT ? fp::add(rae, rde) : rde);
+        o[2 * r + 1] = (STRICT ? fp::add(rao, rdo) : rdo);
     }
     store_out(ur, o[0], o[1], o[2], o[3]);
     store_out(ur + 2, o[4], o[5], o[6], o[7]);
@@ -286,15 +287,16 @@ __device__ __forceinline__ void syn_duo(const T *__restrict__ pa, const T *__res
             rae = fp::mac(rae, c.h[2 * k], wa[G::QA + r - k]);
             rao = fp::mac(rao, c.h[2 * k + 1], wa[G::QA + r - k]);
         }
-        T rde = fp::mul(c.g[1], wd[r]);
-        T rdo = fp::mul(c.g[0], wd[r]);
+        T rde, rdo;      // fast mode: the detail terms continue the approximation's chain (no second FMUL, no final FADD)
+        if constexpr (STRICT) { rde = fp::mul(c.g[1], wd[r]); rdo = fp::mul(c.g[0], wd[r]); }
+        else { rde = fp::mac(rae, c.g[1], wd[r]); rdo = fp::mac(rao, c.g[0], wd[r]); }
 #pragma unroll
         for (int k = 1; k < Q; ++k) {
             rde = fp::mac(rde, c.g[2 * k + 1], wd[r + k]);
             rdo = fp::mac(rdo, c.g[2 * k], wd[r + k]);
         }
-        o[2 * r] = fp::add(rae, rde);
-        o[2 * r + 1] = fp::add(rao, rdo);
+        o[2 * r] = (STRICT ? fp::add(rae, rde) : rde);
+        o[2 * r + 1] = (STRICT ? fp::add(rao, rdo) : rdo);
     }
     store_out(ur, o[0], o[1], o[2], o[3]);
 }

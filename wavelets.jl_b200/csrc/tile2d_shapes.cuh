@@ -176,20 +176,22 @@ __device__ __forceinline__ void fir_syn_regs(T (&s)[NP], T (&d)[NP], const FirCo
     T o0[NP], o1[NP];
 #pragma unroll
     for (int p = H; p < NP - H; ++p) {
+        // STRICT: the two band sums separately, added last (the reference's order); fast mode: the detail terms continue the
+        // approximation's chain (no second FMUL, no final FADD)
         T ra = fp::mul(fc.h[F - 2], s[p - H]);
 #pragma unroll
         for (int m = F - 4; m >= 0; m -= 2) ra = fp::mac(ra, fc.h[m], s[p - m / 2]);
-        T rd = fp::mul(fc.g[1], d[p]);
+        T rd = STRICT ? fp::mul(fc.g[1], d[p]) : fp::mac(ra, fc.g[1], d[p]);
 #pragma unroll
         for (int m = 3; m < F; m += 2) rd = fp::mac(rd, fc.g[m], d[p + (m - 1) / 2]);
-        o0[p] = fp::add(ra, rd);
+        o0[p] = STRICT ? fp::add(ra, rd) : rd;
         ra = fp::mul(fc.h[F - 1], s[p - H]);
 #pragma unroll
         for (int m = F - 3; m >= 1; m -= 2) ra = fp::mac(ra, fc.h[m], s[p - (m - 1) / 2]);
-        rd = fp::mul(fc.g[0], d[p]);
+        rd = STRICT ? fp::mul(fc.g[0], d[p]) : fp::mac(ra, fc.g[0], d[p]);
 #pragma unroll
         for (int m = 2; m < F; m += 2) rd = fp::mac(rd, fc.g[m], d[p + m / 2]);
-        o1[p] = fp::add(ra, rd);
+        o1[p] = STRICT ? fp::add(ra, rd) : rd;
     }
 #pragma unroll
     for (int p = H; p < NP - H; ++p) { s[p] = o0[p]; d[p] = o1[p]; }
