@@ -65,7 +65,10 @@ typedef enum {
 
 /* flags */
 #define WB200_FLAG_STRICT_FP 1u     /* no FMA contraction: results are bit-identical to the reference CPU path
-                                       (same operation order, separately rounded multiply and add) */
+                                       (same operation order, separately rounded multiply and add).  Without the flag:
+                                       the same order with FMAs, one accumulation chain per synthesis output, and the
+                                       last four levels of a full-depth packet tree as one 16 x 16 map per node --
+                                       within the reference's own Float32 GPU tolerance (1e-5, test/gpu.jl:24) */
 #define WB200_FLAG_FORCE_GENERIC 2u /* bypass the fused sm_100a kernels (testing / A-B comparison) */
 
 #define WB200_MAX_FILTER_LEN 64

@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(512)
 k_syn_tiles(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restrict__ x, int64_t n0, int lvl0,
             T *__restrict__ dst, int64_t dst_stride,
             const __grid_constant__ Taps<T, F> c, const __grid_constant__ SynPlan pl,
-            const __grid_constant__ ThreshEpi epi, int thr_a, int pf) {
+            const __grid_constant__ ThreshEpi epi, int thr_a, int pf, int pfl) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     T *sm = reinterpret_cast<T *>(smem_raw + 128);
@@ -232,7 +232,7 @@ k_syn_tiles(const T *__restrict__ asrc, int64_t asrc_stride, const T *__restrict
         if (pcol < gridDim.y) {
             const unsigned pt = lin - pcol * gridDim.x;                 // tile index inside the column
             const T *pxc = x + (int64_t)pcol * n0;
-            for (int l = 1; l <= K; ++l) {
+            for (int l = 1; l <= K && l <= pfl; ++l) {      // pfl: deepest level whose slices are prefetched (WB200_F1D_PREFETCH_INV_LEVELS)
                 const unsigned grp = 1u << ((l - 1) < 3 ? (l - 1) : 3);
                 if (pt & (grp - 1)) continue;
                 const int64_t len = ncur >> l;
@@ -679,7 +679,7 @@ static int32_t run_fused_1d(const PassOp<T> &op, T *y, const T *x, int64_t n, in
             {
                 LaunchScope scope("fused_syn_tiles", st);
                 const int pfv = ((uint64_t)grid.x * grid.y + (uint64_t)tile_prefetch(false) < 0x7fffffffULL) ? tile_prefetch(false) : 0;
-                kern<<<grid, tile_threads(false), smem, st>>>(asrc, astride, x, n, sg.lv0, dst, dstride, taps, pl, op.epi, last_overall ? 1 : 0, pfv);
+                kern<<<grid, tile_threads(false), smem, st>>>(asrc, astride, x, n, sg.lv0, dst, dstride, taps, pl, op.epi, last_overall ? 1 : 0, pfv, env_int("WB200_F1D_PREFETCH_INV_LEVELS", MAXK));
             }
             if (!check_launch("fused_syn_tiles")) { rc = WB200_ECUDA; return finish(); }
         }
