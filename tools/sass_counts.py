@@ -3,6 +3,7 @@
 "What proves a Blackwell-native kernel") counted from `cuobjdump -sass` of the built library, next to the `-Xptxas -v`
 resource lines of the same build.     python tools/sass_counts.py > profiles/r02_sass_counts.md
     UBLKCP   = cp.async.bulk (1-D TMA bulk copy)          UTMALDG = cp.async.bulk.tensor (tensor-map TMA load)
+    UBLKPF   = cp.async.bulk.prefetch.L2 (software prefetch of a future tile into L2)
     LDGSTS   = cp.async (16-byte global -> shared, the one-pass 3-D loader: periodic wrap per chunk)
     SYNCS    = mbarrier arrive / try_wait                  LDS.128 / STS.128 = 16-byte shared-memory accesses
     STG.E.128 (+ .EF = evict-first) = 16-byte global stores;   LDG.E.128 = 16-byte global loads;   FFMA / DFMA = the arithmetic"""
@@ -15,7 +16,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "wavelets.jl_b200", "lib", "libwavelets_b200.so")
-PATS = [("UBLKCP", r"\bUBLKCP"), ("UTMALDG", r"\bUTMALDG"), ("SYNCS", r"\bSYNCS"), ("LDGSTS", r"\bLDGSTS"), ("LDS.128", r"\bLDS\.128"), ("STS.128", r"\bSTS\.128"),
+PATS = [("UBLKCP", r"\bUBLKCP"), ("UBLKPF", r"\bUBLKPF"), ("UTMALDG", r"\bUTMALDG"), ("SYNCS", r"\bSYNCS"), ("LDGSTS", r"\bLDGSTS"), ("LDS.128", r"\bLDS\.128"), ("STS.128", r"\bSTS\.128"),
         ("LDG.E.128", r"\bLDG\.E\.128"), ("STG.E.128", r"\bSTG\.E\.128"), ("STG.E.EF.128", r"\bSTG\.E\.EF\.128"),
         ("STG.E.EF.64", r"\bSTG\.E\.EF\.64"), ("FFMA", r"\bFFMA"), ("DFMA", r"\bDFMA"), ("BAR.SYNC", r"\bBAR\.SYNC")]
 
